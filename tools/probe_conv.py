@@ -1,0 +1,122 @@
+"""GPU bring-up probe for K1 (run with gpurun): conv3x3 tcgen05 kernel vs a numpy fp32 reference.
+
+usage: python tools/probe_conv.py <group>   groups: basic halo dx3 shapes epi special bench
+Each group is its own process so one trapped kernel does not poison the others.
+"""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from video_restore_b200 import _lib  # noqa: E402
+
+
+def ref_conv(x, w, b=None):
+    """x [H,W,Cin] (already fp16-rounded), w [Cout,Cin,3,3] (fp16-rounded) -> [H,W,Cout] fp32, zero pad 1."""
+    H, W, cin = x.shape
+    xp = np.zeros((H + 2, W + 2, cin), np.float32)
+    xp[1:-1, 1:-1] = x
+    y = np.zeros((H, W, w.shape[0]), np.float32)
+    for dy in range(3):
+        for dx in range(3):
+            y += (xp[dy:dy + H, dx:dx + W].reshape(-1, cin) @ w[:, :, dy, dx].T).reshape(H, W, -1)
+    if b is not None:
+        y += b
+    return y
+
+
+def h16(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+def case(name, H, W, cin, cout, seed=0, act=0, prelu=False, res=0, **kw):
+    rng = np.random.default_rng(seed)
+    x = h16(rng.standard_normal((H, W, cin)).astype(np.float32))
+    w = h16((rng.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
+    b = rng.standard_normal(cout).astype(np.float32) * 0.1
+    pr = (rng.random(cout).astype(np.float32) * 0.5) if prelu else None
+    r1 = h16(rng.standard_normal((H, W, cout)).astype(np.float32)) if res >= 1 else None
+    r2 = h16(rng.standard_normal((H, W, cout)).astype(np.float32)) if res >= 2 else None
+    ref = ref_conv(x, w, b)
+    if act == 1:
+        ref = np.where(ref > 0, ref, ref * 0.2)
+    if act == 2:
+        ref = np.where(ref > 0, ref, ref * pr)
+    if r1 is not None:
+        ref = ref * 0.2 + r1
+    if r2 is not None:
+        ref = ref * 0.2 + r2
+    if cout == 48:  # pixel shuffle 4 + nearest base (first 3 input channels)
+        ps = ref.reshape(H, W, 3, 4, 4).transpose(0, 3, 1, 4, 2).reshape(4 * H, 4 * W, 3)
+        base = np.repeat(np.repeat(x[:, :, :3], 4, axis=0), 4, axis=1)
+        ref = ps + base
+    t0 = time.time()
+    try:
+        y, ms = _lib.conv3x3(x, w, b, act=2 if prelu else act, prelu=pr, res1=r1, s1=0.2, res2=r2, s2=0.2, **kw)
+    except Exception as e:  # noqa: BLE001
+        print(f"[{name}] ERROR {e}", flush=True)
+        return False
+    err = np.abs(y - ref)
+    tol = 2e-2 + 4e-3 * np.abs(ref)
+    ok = bool((err <= tol).all())
+    print(f"[{name}] H={H} W={W} cin={cin} cout={cout} kw={kw} max_err={err.max():.4e} "
+          f"mean_err={err.mean():.3e} ref_rms={np.sqrt((ref**2).mean()):.3f} ok={ok} ({time.time()-t0:.1f}s)",
+          flush=True)
+    if not ok:
+        bad = np.argwhere(err > tol)
+        print(f"    mismatches: {len(bad)} of {err.size}; first: {bad[:6].tolist()}", flush=True)
+        ys, xs = np.unique(bad[:, 0]), np.unique(bad[:, 1])
+        print(f"    bad rows {ys[:12].tolist()}.. bad cols {xs[:12].tolist()}..", flush=True)
+    return ok
+
+
+def main():
+    group = sys.argv[1] if len(sys.argv) > 1 else "basic"
+    # only the conv hooks exist in early bring-up builds
+    if "--partial" in sys.argv:
+        keep = ("vr_conv3x3_test", "vr_global_error", "vr_conv3x3_bench")
+        _lib.SIGNATURES = {k: v for k, v in _lib.SIGNATURES.items() if k in keep}
+    if group == "basic":
+        case("halo-nocoll", 8, 128, 32, 32, use_collector=0)
+        case("halo-coll", 8, 128, 32, 32, use_collector=1)
+        case("halo-2chunk", 8, 128, 64, 32, use_collector=0)
+    elif group == "dx3":
+        case("dx3", 8, 128, 32, 32, a_mode=1, use_collector=0)
+        case("dx3-64", 8, 128, 64, 64, a_mode=1, use_collector=0)
+    elif group == "shapes":
+        case("multi-tile", 37, 300, 64, 32)
+        case("cin96", 16, 256, 96, 32)
+        case("cin160", 16, 256, 160, 32)
+        case("cin192-64", 21, 200, 192, 64)
+        case("rows8", 40, 256, 128, 32, rows=8)
+        case("small", 5, 17, 64, 64)
+        case("wide", 9, 1280, 64, 64)
+    elif group == "epi":
+        case("lrelu", 12, 140, 64, 32, act=1)
+        case("prelu", 12, 140, 64, 64, prelu=True)
+        case("res1", 12, 140, 192, 64, res=1)
+        case("res2", 12, 140, 192, 64, res=2)
+    elif group == "special":
+        case("cin3", 12, 140, 3, 64)
+        case("cin12", 12, 140, 12, 64)
+        case("rgb", 12, 140, 64, 3)
+        case("ps4", 12, 140, 64, 48)
+    elif group == "bench":
+        H, W = 720, 1280
+        for cin, cout in [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64), (64, 64)]:
+            for rows, coll in [(4, 0), (4, 1), (8, 1)]:
+                if rows == 8 and cout != 32:
+                    continue
+                try:
+                    ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, use_collector=coll, iters=10)
+                    tf = 2.0 * H * W * cin * cout * 9 / ms / 1e9
+                    print(f"[bench] {cin}->{cout} rows={rows} coll={coll}: {ms:.4f} ms  {tf:.1f} TFLOP/s", flush=True)
+                except Exception as e:  # noqa: BLE001
+                    print(f"[bench] {cin}->{cout} rows={rows} coll={coll}: ERROR {e}", flush=True)
+                    return
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+"""ctypes binding of libvrb200.so (include/vrb200.h). Loading fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libvrb200.so"
+
+VR_MODEL_RRDBNET, VR_MODEL_SRVGG = 0, 1
+VR_BLEND_CROP, VR_BLEND_GAUSSIAN = 0, 1
+
+
+class VrError(RuntimeError):
+    """Raised for any non-zero status from the C ABI (the reference raises Python exceptions per frame,
+    video_upscaler.py:476-481)."""
+
+
+class VrConfig(C.Structure):
+    _fields_ = [
+        ("model_kind", C.c_int32), ("scale", C.c_int32), ("num_block", C.c_int32), ("num_conv", C.c_int32),
+        ("num_feat", C.c_int32), ("num_grow_ch", C.c_int32), ("tile", C.c_int32), ("tile_pad", C.c_int32),
+        ("pre_pad", C.c_int32), ("blend", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 5),
+    ]
+
+
+class VrFrameOpts(C.Structure):
+    _fields_ = [
+        ("denoise", C.c_int32), ("denoise_d", C.c_int32), ("denoise_sigma_color", C.c_float),
+        ("denoise_sigma_space", C.c_float), ("sharpen", C.c_float), ("clahe", C.c_int32),
+        ("clahe_clip", C.c_float), ("clahe_grid", C.c_int32), ("temporal", C.c_int32),
+        ("temporal_alpha", C.c_float), ("temporal_tau", C.c_float), ("reserved", C.c_int32 * 5),
+    ]
+
+
+class VrConvTest(C.Structure):
+    _fields_ = [
+        ("H", C.c_int32), ("W", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+        ("x", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("act", C.c_int32), ("slope", C.c_float), ("prelu", C.c_void_p),
+        ("res1", C.c_void_p), ("s1", C.c_float), ("res2", C.c_void_p), ("s2", C.c_float),
+        ("y", C.c_void_p), ("a_mode", C.c_int32), ("rows", C.c_int32), ("use_collector", C.c_int32),
+        ("iters", C.c_int32), ("ms", C.c_float), ("device", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); also the list the CPU test checks against the header's declarations
+SIGNATURES = {
+    "vr_create": (C.c_int, [C.POINTER(VrConfig), C.POINTER(C.c_void_p)]),
+    "vr_destroy": (None, [C.c_void_p]),
+    "vr_last_error": (C.c_char_p, [C.c_void_p]),
+    "vr_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "vr_commit_weights": (C.c_int, [C.c_void_p]),
+    "vr_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
+                             C.POINTER(VrFrameOpts)]),
+    "vr_restore_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.POINTER(VrFrameOpts)]),
+    "vr_restore_device_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                          C.c_int64, C.POINTER(VrFrameOpts)]),
+    "vr_sync": (C.c_int, [C.c_void_p]),
+    "vr_stream": (C.c_void_p, [C.c_void_p]),
+    "vr_temporal_reset": (C.c_int, [C.c_void_p]),
+    "vr_temporal_set_prev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "vr_temporal_get_prev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "vr_tile_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "vr_bilateral": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
+                               C.c_float]),
+    "vr_unsharp": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float]),
+    "vr_clahe": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float, C.c_int32,
+                           C.c_void_p, C.c_void_p]),
+    "vr_temporal": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
+                              C.c_float]),
+    "vr_blend_weights": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p]),
+    "vr_conv3x3_test": (C.c_int, [C.POINTER(VrConvTest)]),
+    "vr_global_error": (C.c_char_p, []),
+    "vr_conv3x3_bench": (C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_float)]),
+    "vr_launch_count": (C.c_int64, [C.c_void_p]),
+    "vr_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise (never fall back) if it is missing or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VrError(f"{LIB_PATH} is missing: run `python -m video_restore_b200.build` "
+                      "(the restoration path is CUDA-only; there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is absent
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def global_error() -> str:
+    return (load().vr_global_error() or b"").decode()
+
+
+def check(rc: int, handle=None) -> None:
+    if rc == 0:
+        return
+    lib = load()
+    msg = lib.vr_last_error(handle) if handle else lib.vr_global_error()
+    raise VrError(f"libvrb200 status {rc}: {(msg or b'').decode()}")
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def conv3x3(x, weight, bias=None, act=0, slope=0.2, prelu=None, res1=None, s1=1.0, res2=None, s2=1.0,
+            a_mode=0, rows=0, use_collector=1, iters=1, device=0):
+    """Kernel-level hook: x [H,W,Cin] f32, weight [Cout,Cin,3,3] -> y [H,W,Cout] f32 (cout==48: [4H,4W,3])."""
+    lib = load()
+    x = _f32(x); weight = _f32(weight); bias = _f32(bias); prelu = _f32(prelu); res1 = _f32(res1); res2 = _f32(res2)
+    H, W, cin = x.shape
+    cout = weight.shape[0]
+    y = np.zeros((4 * H, 4 * W, 3) if cout == 48 else (H, W, cout), np.float32)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    t = VrConvTest(H=H, W=W, cin=cin, cout=cout, x=ptr(x), weight=ptr(weight), bias=ptr(bias), act=act,
+                   slope=slope, prelu=ptr(prelu), res1=ptr(res1), s1=s1, res2=ptr(res2), s2=s2, y=ptr(y),
+                   a_mode=a_mode, rows=rows, use_collector=use_collector, iters=iters, ms=0.0, device=device)
+    check(lib.vr_conv3x3_test(C.byref(t)))
+    return y, float(t.ms)
+
+
+def conv3x3_bench(H, W, cin, cout, rows=0, use_collector=1, iters=20, device=0) -> float:
+    lib = load()
+    ms = C.c_float(0)
+    check(lib.vr_conv3x3_bench(device, H, W, cin, cout, rows, use_collector, iters, C.byref(ms)))
+    return float(ms.value)

@@ -1,0 +1,212 @@
+// Host side of K1: weight repacking into the swizzled shared-memory image, TMA tensor-map construction,
+// kernel selection and launch. See conv3x3_sm100.cuh for the kernel.
+#include "conv3x3_sm100.cuh"
+#include "vr_common.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace vr {
+
+void set_error(std::string* sink, const std::string& msg) {
+    if (sink) *sink = msg;
+    global_error() = msg;
+}
+std::string& global_error() {
+    static thread_local std::string e;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency,
+// so the library also loads on the GPU-less build box for the symbol check).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn(std::string* err) {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [&]() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    if (!fn) set_error(err, "cuTensorMapEncodeTiled entry point not available");
+    return fn;
+}
+
+// NHWC fp16 activation tensor as a 4-D map (C, W, H, 1); box = 32 channels x pitch pixels x (rows + 2) lines.
+static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int H, int rows, int a_mode,
+                         CUtensorMap* out) {
+    auto key = std::make_tuple(static_cast<const void*>(ptr), cstride, W, H, rows, a_mode);
+    auto it = dev.tmaps.find(key);
+    if (it != dev.tmaps.end()) {
+        *out = it->second;
+        return 0;
+    }
+    EncodeTiledFn enc = get_encode_fn(dev.err);
+    if (!enc) return -2;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 1};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(W) * cstride * 2,
+                             static_cast<cuuint64_t>(H) * W * cstride * 2};
+    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(a_mode == A_HALO ? 130 : 128),
+                         static_cast<cuuint32_t>(rows + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap tm;
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error(dev.err, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) +
+                               " (C=" + std::to_string(cstride) + " W=" + std::to_string(W) +
+                               " H=" + std::to_string(H) + ")");
+        return -2;
+    }
+    if (dev.tmaps.size() > 4096) dev.tmaps.clear();
+    dev.tmaps[key] = tm;
+    *out = tm;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: OIHW fp32 -> [chunk][tap][n][32 ch] fp16 with the 64 B swizzle applied (16 B unit j of row n
+// lands at unit j ^ ((n >> 1) & 3)), i.e. byte-for-byte what the MMA's B descriptor expects in smem.
+// ------------------------------------------------------------------------------------------------
+int pack_conv_weights(Device& dev, const float* w, const float* bias, const float* prelu, int cin, int cout,
+                      ConvWeights* out) {
+    if (cin <= 0 || cout <= 0 || cout > 64) {
+        set_error(dev.err, "pack_conv_weights: unsupported channel counts");
+        return -1;
+    }
+    ConvWeights cw;
+    cw.cin = cin;
+    cw.cout = cout;
+    cw.npad = (cout + 15) / 16 * 16;
+    cw.nchunks = (cin + 31) / 32;
+    const int N = cw.npad;
+    const size_t elems = static_cast<size_t>(cw.nchunks) * 9 * N * 32;
+    std::vector<__half> img(elems, __float2half(0.f));
+    for (int c = 0; c < cw.nchunks; ++c)
+        for (int t = 0; t < 9; ++t)
+            for (int n = 0; n < cout; ++n)
+                for (int ch = 0; ch < 32; ++ch) {
+                    const int ci = c * 32 + ch;
+                    if (ci >= cin) continue;
+                    const float v = w[(static_cast<size_t>(n) * cin + ci) * 9 + t];
+                    const size_t row = (static_cast<size_t>(c) * 9 + t) * N + n;
+                    const int unit = (ch >> 3) ^ ((n >> 1) & 3);
+                    img[row * 32 + unit * 8 + (ch & 7)] = __float2half_rn(v);
+                }
+    VR_CUDA_CHECK(cudaMalloc(&cw.wpack, elems * sizeof(__half)), dev.err);
+    VR_CUDA_CHECK(cudaMemcpyAsync(cw.wpack, img.data(), elems * sizeof(__half), cudaMemcpyHostToDevice, dev.stream),
+                  dev.err);
+    std::vector<float> b(cout, 0.f);
+    if (bias) std::memcpy(b.data(), bias, cout * sizeof(float));
+    VR_CUDA_CHECK(cudaMalloc(&cw.bias, cout * sizeof(float)), dev.err);
+    VR_CUDA_CHECK(cudaMemcpyAsync(cw.bias, b.data(), cout * sizeof(float), cudaMemcpyHostToDevice, dev.stream),
+                  dev.err);
+    if (prelu) {
+        VR_CUDA_CHECK(cudaMalloc(&cw.prelu, cout * sizeof(float)), dev.err);
+        VR_CUDA_CHECK(cudaMemcpyAsync(cw.prelu, prelu, cout * sizeof(float), cudaMemcpyHostToDevice, dev.stream),
+                      dev.err);
+    }
+    VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);  // host staging vectors die here
+    *out = cw;
+    return 0;
+}
+
+void free_conv_weights(ConvWeights* w) {
+    if (w->wpack) cudaFree(w->wpack);
+    if (w->bias) cudaFree(w->bias);
+    if (w->prelu) cudaFree(w->prelu);
+    *w = ConvWeights();
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+template <int N, int TH, int AMODE>
+static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
+    using T = ConvTraits<N, TH, AMODE>;
+    auto kern = conv3x3_tc_kernel<N, TH, AMODE>;
+    static bool attr_done[64] = {};
+    if (!attr_done[dev.ordinal & 63]) {
+        VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes), dev.err);
+        attr_done[dev.ordinal & 63] = true;
+    }
+    a.tiles_x = (a.W + 127) / 128;
+    a.tiles_y = (a.H + TH - 1) / TH;
+    const int tiles = a.tiles_x * a.tiles_y;
+    const int grid = tiles < dev.sm_count ? tiles : dev.sm_count;
+    kern<<<grid, 192, T::kSmemBytes, dev.stream>>>(tm, a);
+    VR_CUDA_CHECK(cudaGetLastError(), dev.err);
+    dev.launches++;
+    return 0;
+}
+
+int run_conv(Device& dev, const ConvCall& c) {
+    const ConvWeights& w = *c.w;
+    if (c.in_cstride % 8 != 0 || c.cin_off % 8 != 0 || c.cin_off + w.nchunks * 32 > c.in_cstride) {
+        set_error(dev.err, "run_conv: input channel slice not addressable (cstride/offset/chunks)");
+        return -1;
+    }
+    int rows = c.rows;
+    if (rows == 0) rows = (c.a_mode == A_HALO) ? 4 : 2;
+    CUtensorMap tm;
+    int rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, rows, c.a_mode, &tm);
+    if (rc) return rc;
+    ConvArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.W = c.W;
+    a.H = c.H;
+    a.nchunks = w.nchunks;
+    a.cin_off = c.cin_off;
+    a.wpack = w.wpack;
+    a.bias = w.bias;
+    a.prelu = w.prelu;
+    a.act = c.act;
+    a.slope = c.slope;
+    a.out = c.out;
+    a.out_cstride = c.out_cstride;
+    a.out_coff = c.out_coff;
+    a.cout = w.cout;
+    a.res1 = c.res1;
+    a.res1_cstride = c.res1_cstride;
+    a.res1_coff = c.res1_coff;
+    a.s1 = c.s1;
+    a.res2 = c.res2;
+    a.res2_cstride = c.res2_cstride;
+    a.res2_coff = c.res2_coff;
+    a.s2 = c.s2;
+    a.out_mode = c.out_mode;
+    a.base = c.base;
+    a.base_cstride = c.base_cstride;
+    a.use_collector = c.use_collector;
+    if (c.out_mode == OUT_NHWC && (w.cout % 16 != 0 || c.out_cstride % 8 != 0 || c.out_coff % 8 != 0)) {
+        set_error(dev.err, "run_conv: NHWC output needs cout % 16 == 0 and 16-byte aligned channel slices");
+        return -1;
+    }
+    if (c.out_mode == OUT_PS4 && w.npad != 48) {
+        set_error(dev.err, "run_conv: pixel-shuffle output needs cout == 48");
+        return -1;
+    }
+    const int key = w.npad * 100 + rows * 10 + c.a_mode;
+    switch (key) {
+        case 16 * 100 + 4 * 10 + A_HALO: return launch_one<16, 4, A_HALO>(dev, tm, a);
+        case 32 * 100 + 4 * 10 + A_HALO: return launch_one<32, 4, A_HALO>(dev, tm, a);
+        case 32 * 100 + 8 * 10 + A_HALO: return launch_one<32, 8, A_HALO>(dev, tm, a);
+        case 48 * 100 + 4 * 10 + A_HALO: return launch_one<48, 4, A_HALO>(dev, tm, a);
+        case 64 * 100 + 4 * 10 + A_HALO: return launch_one<64, 4, A_HALO>(dev, tm, a);
+        case 32 * 100 + 2 * 10 + A_DX3: return launch_one<32, 2, A_DX3>(dev, tm, a);
+        case 64 * 100 + 2 * 10 + A_DX3: return launch_one<64, 2, A_DX3>(dev, tm, a);
+        default:
+            set_error(dev.err, "run_conv: no kernel instantiation for N=" + std::to_string(w.npad) +
+                                   " rows=" + std::to_string(rows) + " a_mode=" + std::to_string(c.a_mode));
+            return -1;
+    }
+}
+
+}  // namespace vr

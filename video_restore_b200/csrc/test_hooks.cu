@@ -1,0 +1,215 @@
+// Kernel-level test and micro-benchmark entry points of the C ABI (vr_conv3x3_test, vr_conv3x3_bench).
+// They exercise exactly the kernels the product path launches; there is no alternative implementation here.
+#include "../../include/vrb200.h"
+#include "conv3x3_sm100.cuh"
+#include "vr_common.h"
+
+#include <cstring>
+#include <vector>
+
+using namespace vr;
+
+extern "C" const char* vr_global_error(void) { return global_error().c_str(); }
+
+namespace {
+struct ScopedDev {
+    Device dev;
+    std::string err;
+    bool ok = false;
+    explicit ScopedDev(int ordinal) {
+        dev.err = &err;
+        dev.ordinal = ordinal;
+        if (cudaSetDevice(ordinal) != cudaSuccess) {
+            set_error(&err, "cudaSetDevice failed (no usable CUDA device; this library has no CPU path)");
+            return;
+        }
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, ordinal) != cudaSuccess) {
+            set_error(&err, "cudaGetDeviceProperties failed");
+            return;
+        }
+        if (p.major != 10) {
+            set_error(&err, "device is not sm_100 class (found sm_" + std::to_string(p.major * 10 + p.minor) + ")");
+            return;
+        }
+        dev.sm_count = p.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error(&err, "cudaStreamCreate failed");
+            return;
+        }
+        ok = true;
+    }
+    ~ScopedDev() {
+        if (dev.stream) cudaStreamDestroy(dev.stream);
+    }
+};
+
+std::vector<__half> to_half_padded(const float* x, size_t px, int c, int cpad) {
+    std::vector<__half> h(px * cpad, __float2half(0.f));
+    for (size_t p = 0; p < px; ++p)
+        for (int i = 0; i < c; ++i) h[p * cpad + i] = __float2half_rn(x[p * c + i]);
+    return h;
+}
+}  // namespace
+
+extern "C" int vr_conv3x3_test(vr_conv_test* t) {
+    if (!t || !t->x || !t->weight || !t->y || t->H <= 0 || t->W <= 0) {
+        set_error(nullptr, "vr_conv3x3_test: bad arguments");
+        return VR_E_INVALID;
+    }
+    ScopedDev sd(t->device);
+    if (!sd.ok) return VR_E_NODEVICE;
+    Device& dev = sd.dev;
+    const size_t px = static_cast<size_t>(t->H) * t->W;
+    const int cin_pad = (t->cin + 31) / 32 * 32;
+    const int cout = t->cout;
+    const bool rgb4 = (cout == 3);
+    const bool ps4 = (cout == 48);
+    const int out_c = rgb4 ? 4 : cout;
+
+    ConvWeights w;
+    int rc = pack_conv_weights(dev, t->weight, t->bias, t->act == ACT_PRELU ? t->prelu : nullptr, t->cin, cout, &w);
+    if (rc) return rc;
+
+    std::vector<__half> hx = to_half_padded(t->x, px, t->cin, cin_pad);
+    __half *dx = nullptr, *dy = nullptr, *dr1 = nullptr, *dr2 = nullptr;
+    const size_t out_elems = ps4 ? px * 16 * 4 : px * out_c;
+    VR_CUDA_CHECK(cudaMalloc(&dx, hx.size() * sizeof(__half)), dev.err);
+    VR_CUDA_CHECK(cudaMalloc(&dy, out_elems * sizeof(__half)), dev.err);
+    VR_CUDA_CHECK(cudaMemset(dy, 0, out_elems * sizeof(__half)), dev.err);
+    VR_CUDA_CHECK(cudaMemcpy(dx, hx.data(), hx.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
+    if (t->res1) {
+        std::vector<__half> h = to_half_padded(t->res1, px, cout, cout);
+        VR_CUDA_CHECK(cudaMalloc(&dr1, h.size() * sizeof(__half)), dev.err);
+        VR_CUDA_CHECK(cudaMemcpy(dr1, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
+    }
+    if (t->res2) {
+        std::vector<__half> h = to_half_padded(t->res2, px, cout, cout);
+        VR_CUDA_CHECK(cudaMalloc(&dr2, h.size() * sizeof(__half)), dev.err);
+        VR_CUDA_CHECK(cudaMemcpy(dr2, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
+    }
+
+    ConvCall c;
+    c.in = dx;
+    c.in_cstride = cin_pad;
+    c.H = t->H;
+    c.W = t->W;
+    c.w = &w;
+    c.act = t->act;
+    c.slope = t->slope;
+    c.out = dy;
+    c.out_cstride = out_c;
+    c.out_coff = 0;
+    c.res1 = dr1;
+    c.res1_cstride = cout;
+    c.s1 = t->s1;
+    c.res2 = dr2;
+    c.res2_cstride = cout;
+    c.s2 = t->s2;
+    c.out_mode = rgb4 ? OUT_RGB4 : (ps4 ? OUT_PS4 : OUT_NHWC);
+    c.base = dx;
+    c.base_cstride = cin_pad;
+    c.a_mode = t->a_mode;
+    c.rows = t->rows;
+    c.use_collector = t->use_collector;
+
+    const int iters = t->iters > 0 ? t->iters : 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    rc = run_conv(dev, c);  // warm-up and the run whose result is returned when iters == 1
+    if (rc == 0) {
+        cudaEventRecord(e0, dev.stream);
+        for (int i = 1; i < iters && rc == 0; ++i) rc = run_conv(dev, c);
+        cudaEventRecord(e1, dev.stream);
+    }
+    cudaError_t se = cudaStreamSynchronize(dev.stream);
+    if (rc == 0 && se != cudaSuccess) {
+        set_error(dev.err, std::string("conv kernel failed: ") + cudaGetErrorString(se));
+        rc = VR_E_CUDA;
+    }
+    if (rc == 0) {
+        float ms = 0.f;
+        if (iters > 1) {
+            cudaEventElapsedTime(&ms, e0, e1);
+            ms /= (iters - 1);
+        }
+        t->ms = ms;
+        std::vector<__half> hy(out_elems);
+        cudaMemcpy(hy.data(), dy, out_elems * sizeof(__half), cudaMemcpyDeviceToHost);
+        if (ps4) {
+            // [4H][4W][4] fp16 -> y[4H][4W][3] fp32
+            for (size_t i = 0; i < px * 16; ++i)
+                for (int ch = 0; ch < 3; ++ch) t->y[i * 3 + ch] = __half2float(hy[i * 4 + ch]);
+        } else {
+            for (size_t p = 0; p < px; ++p)
+                for (int ch = 0; ch < cout; ++ch) t->y[p * cout + ch] = __half2float(hy[p * out_c + ch]);
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dx);
+    cudaFree(dy);
+    if (dr1) cudaFree(dr1);
+    if (dr2) cudaFree(dr2);
+    free_conv_weights(&w);
+    return rc;
+}
+
+extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t rows,
+                                int32_t use_collector, int32_t iters, float* ms_out) {
+    ScopedDev sd(device);
+    if (!sd.ok) return VR_E_NODEVICE;
+    Device& dev = sd.dev;
+    const size_t px = static_cast<size_t>(H) * W;
+    const int cin_pad = (cin + 31) / 32 * 32;
+    std::vector<float> w(static_cast<size_t>(cout) * cin * 9);
+    uint32_t s = 12345u;
+    for (auto& v : w) {
+        s = s * 1664525u + 1013904223u;
+        v = (static_cast<float>(s >> 8) / 16777216.f - 0.5f) * 0.05f;
+    }
+    ConvWeights cw;
+    int rc = pack_conv_weights(dev, w.data(), nullptr, nullptr, cin, cout, &cw);
+    if (rc) return rc;
+    __half *dx = nullptr, *dy = nullptr;
+    const int out_c = (cout == 3) ? 4 : cout;
+    VR_CUDA_CHECK(cudaMalloc(&dx, px * cin_pad * sizeof(__half)), dev.err);
+    VR_CUDA_CHECK(cudaMalloc(&dy, px * out_c * sizeof(__half)), dev.err);
+    VR_CUDA_CHECK(cudaMemset(dx, 0x11, px * cin_pad * sizeof(__half)), dev.err);  // small finite fp16 values
+    ConvCall c;
+    c.in = dx;
+    c.in_cstride = cin_pad;
+    c.H = H;
+    c.W = W;
+    c.w = &cw;
+    c.act = ACT_LRELU;
+    c.out = dy;
+    c.out_cstride = out_c;
+    c.out_mode = (cout == 3) ? OUT_RGB4 : OUT_NHWC;
+    c.rows = rows;
+    c.use_collector = use_collector;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3 && rc == 0; ++i) rc = run_conv(dev, c);
+    cudaEventRecord(e0, dev.stream);
+    for (int i = 0; i < iters && rc == 0; ++i) rc = run_conv(dev, c);
+    cudaEventRecord(e1, dev.stream);
+    cudaError_t se = cudaStreamSynchronize(dev.stream);
+    if (rc == 0 && se != cudaSuccess) {
+        set_error(dev.err, std::string("conv bench kernel failed: ") + cudaGetErrorString(se));
+        rc = VR_E_CUDA;
+    }
+    if (rc == 0) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out = ms / iters;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dx);
+    cudaFree(dy);
+    free_conv_weights(&cw);
+    return rc;
+}

@@ -1,0 +1,102 @@
+// Host-side shared declarations for libvrb200.so (not part of the public ABI; see include/vrb200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace vr {
+
+// ---- error plumbing: every internal function returns 0 / VR_E_* and records a message ----
+void set_error(std::string* sink, const std::string& msg);
+std::string& global_error();
+
+#define VR_CUDA_CHECK(expr, sink)                                                                   \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::vr::set_error((sink), std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+            return -2;                                                                              \
+        }                                                                                           \
+    } while (0)
+
+// ---- packed conv layer ----
+struct ConvWeights {
+    int cin = 0, cout = 0;
+    int npad = 0;     // GEMM N: cout rounded up to 16
+    int nchunks = 0;  // ceil(cin / 32)
+    __half* wpack = nullptr;  // device, [nchunks][9][npad][32] swizzled
+    float* bias = nullptr;    // device [cout]
+    float* prelu = nullptr;   // device [cout] or null
+};
+
+struct ConvCall {
+    const __half* in = nullptr;  // NHWC fp16
+    int in_cstride = 0;          // channels per pixel of the source buffer
+    int cin_off = 0;
+    int H = 0, W = 0;
+    const ConvWeights* w = nullptr;
+    int act = 0;
+    float slope = 0.2f;
+    __half* out = nullptr;
+    int out_cstride = 0, out_coff = 0;
+    const __half* res1 = nullptr;
+    int res1_cstride = 0, res1_coff = 0;
+    float s1 = 1.f;
+    const __half* res2 = nullptr;
+    int res2_cstride = 0, res2_coff = 0;
+    float s2 = 1.f;
+    int out_mode = 0;  // ConvOut
+    const __half* base = nullptr;
+    int base_cstride = 0;
+    int a_mode = 0;  // ConvAMode
+    int rows = 0;    // TH, 0 = default
+    int use_collector = 1;
+};
+
+struct Device {
+    int ordinal = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string* err = nullptr;
+    int64_t launches = 0;
+    // tensor-map cache: (ptr, cstride, W, H, rows, a_mode)
+    std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
+};
+
+int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const float* prelu, int cin, int cout,
+                      ConvWeights* out);
+void free_conv_weights(ConvWeights* w);
+int run_conv(Device& dev, const ConvCall& c);
+
+// ---- elementwise / filter kernels (kernels_frame.cu) ----
+int launch_upsample2x(Device& dev, const __half* src, int H, int W, int C, __half* dst);
+// u8 BGR frame rect -> fp16 RGB NHWC32 (zero padded channels); reflect pads past the frame edge;
+// unshuffle=1 applies pixel_unshuffle(2) (12 channels, c*4 + dy*2 + dx)
+int launch_pre(Device& dev, const uint8_t* frame, int64_t stride, int H, int W, int x0, int y0, int w, int h,
+               int unshuffle, __half* dst);
+// RGB4 fp16 tile -> clamp, *255, rint, BGR u8 into the frame rect
+int launch_post_crop(Device& dev, const __half* tile, int tile_w, int crop_x0, int crop_y0, int w, int h,
+                     uint8_t* frame, int64_t stride, int dst_x0, int dst_y0);
+
+struct BlendTile {
+    const __half* data;  // RGB4 fp16 [ph][pw]
+    int px0, py0, pw, ph;  // padded output rect in the scaled frame
+};
+int launch_post_blend(Device& dev, const std::vector<BlendTile>& tiles, int tiles_x, int tiles_y, int tile_out,
+                      int pad_out, uint8_t* frame, int64_t stride, int sH, int sW, void* d_tile_table);
+int launch_bilateral(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
+                     int d, float sigma_color, float sigma_space);
+int launch_unsharp(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
+                   float amount);
+int launch_clahe(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
+                 float clip, int grid, int32_t* d_hist, uint8_t* d_lut, uint8_t* d_luma);
+int launch_temporal(Device& dev, const uint8_t* cur, int64_t cstride, const uint8_t* prev, int64_t pstride, int H,
+                    int W, uint8_t* dst, int64_t dstride, float alpha, float tau);
+int launch_blend_weights(Device& dev, int extent, float* d_w);
+
+}  // namespace vr
