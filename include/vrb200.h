@@ -134,9 +134,8 @@ typedef struct vr_conv_test {
     const float* res2; /* then y = y*s2 + res2 */
     float s2;
     float* y;          /* [H][W][cout] */
-    int32_t a_mode;    /* 0: one haloed TMA box + shifted descriptors, 1: three dx-shifted boxes */
-    int32_t rows;      /* output rows per CTA tile (0 = default) */
-    int32_t use_collector;
+    int32_t rows;      /* output rows per CTA tile (0 = default 4) */
+    int32_t flags;     /* measurement ablations: 1 no A-collector reuse, 2 skip TMA, 4 skip MMA, 8 skip epilogue */
     int32_t iters;     /* >1: repeat the launch and report the average */
     float ms;          /* out: average kernel milliseconds (CUDA events) */
     int32_t device;
@@ -146,7 +145,7 @@ const char* vr_global_error(void);
 
 /* Device-resident conv benchmark on zero-copy synthetic data: returns average ms per launch. */
 int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t rows,
-                     int32_t use_collector, int32_t iters, float* ms_out);
+                     int32_t flags, int32_t iters, float* ms_out);
 
 /* Counters since handle creation: kernels launched by this library, for bench.py's gpu_launches. */
 int64_t vr_launch_count(const vr_handle* h);

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(long long* cycles_out, in
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32 && elect_one()) {
         constexpr uint32_t idesc = make_idesc_f16(128, N);
         const uint32_t a_base = smem_u32(smem);
         const uint32_t b_base = a_base + 128 * 1024;
@@ -45,15 +45,15 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(long long* cycles_out, in
                 const int g = j / 3, m = j % 3;
                 const uint32_t a_off = (MODE == 0) ? (j * 8320u) : (g * 8320u);
                 const uint32_t b_off = (MODE == 3) ? 0u : (j % 3) * N * 64u;
-                const uint64_t ad = make_smem_desc(a_base + a_off, 512, kLayoutSw64);
-                const uint64_t bd = make_smem_desc(b_base + b_off, 512, kLayoutSw64);
+                const uint32_t ad = (a_base >> 4) + (a_off >> 4);
+                const uint32_t bd = (b_base >> 4) + (b_off >> 4);
                 const uint32_t d = tmem + ((g + m) % kDSlots) * N;
                 if (MODE == 1) {
-                    if (m == 0) umma_f16<kCollFill>(d, ad, bd, idesc, 1u);
-                    else if (m == 1) umma_f16<kCollUse>(d, ad, bd, idesc, 1u);
-                    else umma_f16<kCollLastUse>(d, ad, bd, idesc, 1u);
+                    if (m == 0) umma_f16<kCollFill>(d, ad, kDescHiSw64, bd, kDescHiSw64, idesc, 1u);
+                    else if (m == 1) umma_f16<kCollUse>(d, ad, kDescHiSw64, bd, kDescHiSw64, idesc, 1u);
+                    else umma_f16<kCollLastUse>(d, ad, kDescHiSw64, bd, kDescHiSw64, idesc, 1u);
                 } else {
-                    umma_f16<kCollNone>(d, ad, bd, idesc, 1u);
+                    umma_f16<kCollNone>(d, ad, kDescHiSw64, bd, kDescHiSw64, idesc, 1u);
                 }
             }
         }

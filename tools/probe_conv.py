@@ -42,7 +42,7 @@ def case(name, H, W, cin, cout, seed=0, act=0, prelu=False, res=0, **kw):
     ref = ref_conv(x, w, b)
     if act == 1:
         ref = np.where(ref > 0, ref, ref * 0.2)
-    if act == 2:
+    if prelu:
         ref = np.where(ref > 0, ref, ref * pr)
     if r1 is not None:
         ref = ref * 0.2 + r1
@@ -79,12 +79,9 @@ def main():
         keep = ("vr_conv3x3_test", "vr_global_error", "vr_conv3x3_bench")
         _lib.SIGNATURES = {k: v for k, v in _lib.SIGNATURES.items() if k in keep}
     if group == "basic":
-        case("halo-nocoll", 8, 128, 32, 32, use_collector=0)
-        case("halo-coll", 8, 128, 32, 32, use_collector=1)
-        case("halo-2chunk", 8, 128, 64, 32, use_collector=0)
-    elif group == "dx3":
-        case("dx3", 8, 128, 32, 32, a_mode=1, use_collector=0)
-        case("dx3-64", 8, 128, 64, 64, a_mode=1, use_collector=0)
+        case("halo-nocoll", 8, 128, 32, 32, flags=1)
+        case("halo-coll", 8, 128, 32, 32)
+        case("halo-2chunk", 8, 128, 64, 32, flags=1)
     elif group == "shapes":
         case("multi-tile", 37, 300, 64, 32)
         case("cin96", 16, 256, 96, 32)
@@ -105,18 +102,23 @@ def main():
         case("ps4", 12, 140, 64, 48)
     elif group == "bench":
         H, W = 720, 1280
-        for cin, cout in [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64), (64, 64)]:
-            for rows, coll in [(4, 0), (4, 1), (8, 1)]:
+        names = {0: "full", 1: "no-collector", 2: "skip-tma", 4: "skip-mma", 8: "skip-epi", 10: "mma-only",
+                 12: "tma-only", 6: "epi-only"}
+        for cin, cout in [(64, 32), (160, 32), (192, 64), (64, 64)]:
+            for rows in (4, 8):
                 if rows == 8 and cout != 32:
                     continue
-                try:
-                    ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, use_collector=coll, iters=10)
-                    tf = 2.0 * H * W * cin * cout * 9 / ms / 1e9
-                    print(f"[bench] {cin}->{cout} rows={rows} coll={coll}: {ms:.4f} ms  {tf:.1f} TFLOP/s", flush=True)
-                except Exception as e:  # noqa: BLE001
-                    print(f"[bench] {cin}->{cout} rows={rows} coll={coll}: ERROR {e}", flush=True)
-                    return
-
+                for fl in (0, 1, 2, 4, 8, 10, 12, 6):
+                    if fl == 1 and rows == 8:
+                        continue
+                    try:
+                        ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, flags=fl, iters=10)
+                        tf = 2.0 * H * W * cin * cout * 9 / ms / 1e9
+                        print(f"[bench] {cin}->{cout} rows={rows} {names[fl]:>12}: {ms:.4f} ms  {tf:.1f} TFLOP/s",
+                              flush=True)
+                    except Exception as e:  # noqa: BLE001
+                        print(f"[bench] {cin}->{cout} rows={rows} flags={fl}: ERROR {e}", flush=True)
+                        return
 
 if __name__ == "__main__":
     main()

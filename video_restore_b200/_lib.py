@@ -41,7 +41,7 @@ class VrConvTest(C.Structure):
         ("x", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
         ("act", C.c_int32), ("slope", C.c_float), ("prelu", C.c_void_p),
         ("res1", C.c_void_p), ("s1", C.c_float), ("res2", C.c_void_p), ("s2", C.c_float),
-        ("y", C.c_void_p), ("a_mode", C.c_int32), ("rows", C.c_int32), ("use_collector", C.c_int32),
+        ("y", C.c_void_p), ("rows", C.c_int32), ("flags", C.c_int32),
         ("iters", C.c_int32), ("ms", C.c_float), ("device", C.c_int32),
     ]
 
@@ -117,7 +117,7 @@ def _f32(a):
 
 
 def conv3x3(x, weight, bias=None, act=0, slope=0.2, prelu=None, res1=None, s1=1.0, res2=None, s2=1.0,
-            a_mode=0, rows=0, use_collector=1, iters=1, device=0):
+            rows=0, flags=0, iters=1, device=0):
     """Kernel-level hook: x [H,W,Cin] f32, weight [Cout,Cin,3,3] -> y [H,W,Cout] f32 (cout==48: [4H,4W,3])."""
     lib = load()
     x = _f32(x); weight = _f32(weight); bias = _f32(bias); prelu = _f32(prelu); res1 = _f32(res1); res2 = _f32(res2)
@@ -127,13 +127,13 @@ def conv3x3(x, weight, bias=None, act=0, slope=0.2, prelu=None, res1=None, s1=1.
     ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     t = VrConvTest(H=H, W=W, cin=cin, cout=cout, x=ptr(x), weight=ptr(weight), bias=ptr(bias), act=act,
                    slope=slope, prelu=ptr(prelu), res1=ptr(res1), s1=s1, res2=ptr(res2), s2=s2, y=ptr(y),
-                   a_mode=a_mode, rows=rows, use_collector=use_collector, iters=iters, ms=0.0, device=device)
+                   rows=rows, flags=flags, iters=iters, ms=0.0, device=device)
     check(lib.vr_conv3x3_test(C.byref(t)))
     return y, float(t.ms)
 
 
-def conv3x3_bench(H, W, cin, cout, rows=0, use_collector=1, iters=20, device=0) -> float:
+def conv3x3_bench(H, W, cin, cout, rows=0, flags=0, iters=20, device=0) -> float:
     lib = load()
     ms = C.c_float(0)
-    check(lib.vr_conv3x3_bench(device, H, W, cin, cout, rows, use_collector, iters, C.byref(ms)))
+    check(lib.vr_conv3x3_bench(device, H, W, cin, cout, rows, flags, iters, C.byref(ms)))
     return float(ms.value)

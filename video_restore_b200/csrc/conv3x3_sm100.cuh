@@ -25,7 +25,8 @@ namespace vr {
 
 enum ConvAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2 };
 enum ConvOut { OUT_NHWC = 0, OUT_RGB4 = 1, OUT_PS4 = 2 };
-enum ConvAMode { A_HALO = 0, A_DX3 = 1 };
+// debug ablation flags (ConvArgs::flags): measurement only
+enum ConvFlags { FLAG_NO_COLLECTOR = 1, FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8 };
 
 struct ConvArgs {
     int W, H;              // conv input == output extent
@@ -48,20 +49,19 @@ struct ConvArgs {
     int out_mode;
     const __half* base;  // OUT_PS4: network input (RGB in channels 0..2), added to the 16 sub-pixels
     int base_cstride;
-    int use_collector;
+    int flags;  // ConvFlags
 };
 
 constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
 constexpr int next_pow2_c(int x) { int p = 32; while (p < x) p *= 2; return p; }
 
-template <int N, int TH, int AMODE>
+template <int N, int TH>
 struct ConvTraits {
     static constexpr int kInRows = TH + 2;
-    static constexpr int kPitch = (AMODE == A_HALO) ? 130 : 128;
-    static constexpr int kCopies = (AMODE == A_HALO) ? 1 : 3;
+    static constexpr int kPitch = 130;  // 128 output pixels + 1 halo pixel each side
     static constexpr int kCopyBytes = kInRows * kPitch * 64;  // bytes one TMA box delivers
     static constexpr int kCopyStride = round_up_c(kCopyBytes, 1024);
-    static constexpr int kAStage = kCopies * kCopyStride;
+    static constexpr int kAStage = kCopyStride;
     static constexpr int kBBytes = 9 * N * 64;
     static constexpr int kBStage = round_up_c(kBBytes, 1024);
     static constexpr int kStageBytes = kAStage + kBStage;
@@ -100,10 +100,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return q;
 }
 
-template <int N, int TH, int AMODE>
+template <int N, int TH, bool COLL>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
-    using T = ConvTraits<N, TH, AMODE>;
+    using T = ConvTraits<N, TH>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tail = smem + T::kStages * T::kStageBytes;
@@ -155,69 +155,79 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 for (int c = 0; c < a.nchunks; ++c) {
                     ptx::mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * T::kStageBytes;
-                    ptx::mbar_expect_tx(&full[s], T::kCopies * T::kCopyBytes + T::kBBytes);
-#pragma unroll
-                    for (int cp = 0; cp < T::kCopies; ++cp)
-                        ptx::tma_load_4d(st + cp * T::kCopyStride, &tmap, &full[s], a.cin_off + c * 32,
-                                         x0 - 1 + cp, y0 - 1, 0);
-                    ptx::bulk_load(st + T::kAStage, a.wpack + static_cast<size_t>(c) * 9 * N * 32, T::kBBytes,
-                                   &full[s]);
+                    if (a.flags & FLAG_SKIP_TMA) {
+                        ptx::mbar_arrive(&full[s]);
+                    } else {
+                        ptx::mbar_expect_tx(&full[s], T::kCopyBytes + T::kBBytes);
+                        ptx::tma_load_4d(st, &tmap, &full[s], a.cin_off + c * 32, x0 - 1, y0 - 1, 0);
+                        ptx::bulk_load(st + T::kAStage, a.wpack + static_cast<size_t>(c) * 9 * N * 32, T::kBBytes,
+                                       &full[s]);
+                    }
                     if (++s == T::kStages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(128, N);
-            int s = 0;
-            uint32_t ph = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
-                ptx::mbar_wait(&tempty[buf], aph ^ 1);
+        // ===================== MMA issuer =====================
+        // The whole warp walks the (uniform) loop so every address stays on the uniform datapath; one elected
+        // lane issues the tcgen05 instructions and the commits.
+        constexpr uint32_t idesc = ptx::make_idesc_f16(128, N);
+        const bool skip_mma = (a.flags & FLAG_SKIP_MMA) != 0;
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            ptx::mbar_wait(&tempty[buf], aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_base = tmem_base + buf * T::kAccCols;
+            for (int c = 0; c < a.nchunks; ++c) {
+                ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                const uint32_t d_base = tmem_base + buf * T::kAccCols;
-                for (int c = 0; c < a.nchunks; ++c) {
-                    ptx::mbar_wait(&full[s], ph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_base = ptx::smem_u32(smem + s * T::kStageBytes);
-                    const uint32_t b_base = a_base + T::kAStage;
+                if (ptx::elect_one()) {
+                    const uint32_t a_lo0 = (ptx::smem_u32(smem + s * T::kStageBytes) >> 4);
+                    const uint32_t b_lo0 = a_lo0 + (T::kAStage >> 4);
+                    if (!skip_mma) {
 #pragma unroll
-                    for (int rho = 0; rho < T::kInRows; ++rho) {
+                        for (int rho = 0; rho < T::kInRows; ++rho) {
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
+                            for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                const uint32_t a_addr =
-                                    (AMODE == A_HALO) ? a_base + (rho * T::kPitch + dx) * 64 + k * 32
-                                                      : a_base + dx * T::kCopyStride + rho * T::kPitch * 64 + k * 32;
-                                const uint64_t adesc = ptx::make_smem_desc(a_addr, 512, ptx::kLayoutSw64);
-                                constexpr int kDummy = 0;
-                                (void)kDummy;
-                                const int dy_lo = rho - (TH - 1) > 0 ? rho - (TH - 1) : 0;
-                                const int dy_hi = rho < 2 ? rho : 2;
+                                for (int k = 0; k < 2; ++k) {
+                                    const uint32_t a_lo = a_lo0 + (((rho * T::kPitch + dx) * 64 + k * 32) >> 4);
+                                    constexpr int kLast = TH - 1;
+                                    const int dy_lo = rho - kLast > 0 ? rho - kLast : 0;
+                                    const int dy_hi = rho < 2 ? rho : 2;
 #pragma unroll
-                                for (int dy = 0; dy < 3; ++dy) {
-                                    if (dy < dy_lo || dy > dy_hi) continue;
-                                    const int r = rho - dy;
-                                    const uint64_t bdesc = ptx::make_smem_desc(
-                                        b_base + (dy * 3 + dx) * N * 64 + k * 32, 512, ptx::kLayoutSw64);
-                                    const uint32_t acc = (c | dy | dx | k) != 0 ? 1u : 0u;
-                                    int coll = ptx::kCollNone;
-                                    if (a.use_collector && dy_lo != dy_hi)
-                                        coll = (dy == dy_lo) ? ptx::kCollFill
-                                                             : (dy == dy_hi ? ptx::kCollLastUse : ptx::kCollUse);
-                                    ptx::umma_f16_rt(coll, d_base + r * N, adesc, bdesc, idesc, acc);
+                                    for (int dy = 0; dy < 3; ++dy) {
+                                        if (dy < dy_lo || dy > dy_hi) continue;
+                                        const int r = rho - dy;
+                                        const uint32_t b_lo = b_lo0 + ((((dy * 3 + dx) * N) * 64 + k * 32) >> 4);
+                                        const uint32_t acc = (c | dy | dx | k) != 0 ? 1u : 0u;
+                                        const uint32_t d = d_base + r * N;
+                                        if (!COLL || dy_lo == dy_hi)
+                                            ptx::umma_f16<ptx::kCollNone>(d, a_lo, ptx::kDescHiSw64, b_lo,
+                                                                          ptx::kDescHiSw64, idesc, acc);
+                                        else if (dy == dy_lo)
+                                            ptx::umma_f16<ptx::kCollFill>(d, a_lo, ptx::kDescHiSw64, b_lo,
+                                                                          ptx::kDescHiSw64, idesc, acc);
+                                        else if (dy == dy_hi)
+                                            ptx::umma_f16<ptx::kCollLastUse>(d, a_lo, ptx::kDescHiSw64, b_lo,
+                                                                             ptx::kDescHiSw64, idesc, acc);
+                                        else
+                                            ptx::umma_f16<ptx::kCollUse>(d, a_lo, ptx::kDescHiSw64, b_lo,
+                                                                         ptx::kDescHiSw64, idesc, acc);
+                                    }
                                 }
                             }
                         }
                     }
                     ptx::umma_commit(&empty[s]);
-                    if (++s == T::kStages) { s = 0; ph ^= 1; }
+                    if (c == a.nchunks - 1) ptx::umma_commit(&tfull[buf]);
                 }
-                ptx::umma_commit(&tfull[buf]);
+                __syncwarp();
+                if (++s == T::kStages) { s = 0; ph ^= 1; }
             }
         }
     } else {
@@ -232,8 +242,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             ptx::mbar_wait(&tfull[buf], aph);
             ptx::tc_fence_after();
             const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * T::kAccCols;
+            const int r_end = (a.flags & FLAG_SKIP_EPI) ? 0 : TH;
 #pragma unroll 1
-            for (int r = 0; r < TH; ++r) {
+            for (int r = 0; r < r_end; ++r) {
                 const int y = y0 + r;
                 if (y >= a.H) break;  // warp-uniform
                 const size_t p = static_cast<size_t>(y) * a.W + x;

@@ -39,9 +39,8 @@ static EncodeTiledFn get_encode_fn(std::string* err) {
 }
 
 // NHWC fp16 activation tensor as a 4-D map (C, W, H, 1); box = 32 channels x pitch pixels x (rows + 2) lines.
-static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int H, int rows, int a_mode,
-                         CUtensorMap* out) {
-    auto key = std::make_tuple(static_cast<const void*>(ptr), cstride, W, H, rows, a_mode);
+static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int H, int rows, CUtensorMap* out) {
+    auto key = std::make_tuple(static_cast<const void*>(ptr), cstride, W, H, rows);
     auto it = dev.tmaps.find(key);
     if (it != dev.tmaps.end()) {
         *out = it->second;
@@ -52,8 +51,7 @@ static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 1};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(W) * cstride * 2,
                              static_cast<cuuint64_t>(H) * W * cstride * 2};
-    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(a_mode == A_HALO ? 130 : 128),
-                         static_cast<cuuint32_t>(rows + 2), 1};
+    cuuint32_t box[4] = {32, 130, static_cast<cuuint32_t>(rows + 2), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(ptr), dims, strides, box, estr,
@@ -128,10 +126,10 @@ void free_conv_weights(ConvWeights* w) {
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
-template <int N, int TH, int AMODE>
+template <int N, int TH, bool COLL>
 static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
-    using T = ConvTraits<N, TH, AMODE>;
-    auto kern = conv3x3_tc_kernel<N, TH, AMODE>;
+    using T = ConvTraits<N, TH>;
+    auto kern = conv3x3_tc_kernel<N, TH, COLL>;
     static bool attr_done[64] = {};
     if (!attr_done[dev.ordinal & 63]) {
         VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes), dev.err);
@@ -154,9 +152,9 @@ int run_conv(Device& dev, const ConvCall& c) {
         return -1;
     }
     int rows = c.rows;
-    if (rows == 0) rows = (c.a_mode == A_HALO) ? 4 : 2;
+    if (rows == 0) rows = 4;
     CUtensorMap tm;
-    int rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, rows, c.a_mode, &tm);
+    int rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, rows, &tm);
     if (rc) return rc;
     ConvArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -184,7 +182,7 @@ int run_conv(Device& dev, const ConvCall& c) {
     a.out_mode = c.out_mode;
     a.base = c.base;
     a.base_cstride = c.base_cstride;
-    a.use_collector = c.use_collector;
+    a.flags = c.flags;
     if (c.out_mode == OUT_NHWC && (w.cout % 16 != 0 || c.out_cstride % 8 != 0 || c.out_coff % 8 != 0)) {
         set_error(dev.err, "run_conv: NHWC output needs cout % 16 == 0 and 16-byte aligned channel slices");
         return -1;
@@ -193,18 +191,19 @@ int run_conv(Device& dev, const ConvCall& c) {
         set_error(dev.err, "run_conv: pixel-shuffle output needs cout == 48");
         return -1;
     }
-    const int key = w.npad * 100 + rows * 10 + c.a_mode;
+    const int coll = (c.flags & FLAG_NO_COLLECTOR) ? 0 : 1;
+    const int key = w.npad * 100 + rows * 10 + coll;
     switch (key) {
-        case 16 * 100 + 4 * 10 + A_HALO: return launch_one<16, 4, A_HALO>(dev, tm, a);
-        case 32 * 100 + 4 * 10 + A_HALO: return launch_one<32, 4, A_HALO>(dev, tm, a);
-        case 32 * 100 + 8 * 10 + A_HALO: return launch_one<32, 8, A_HALO>(dev, tm, a);
-        case 48 * 100 + 4 * 10 + A_HALO: return launch_one<48, 4, A_HALO>(dev, tm, a);
-        case 64 * 100 + 4 * 10 + A_HALO: return launch_one<64, 4, A_HALO>(dev, tm, a);
-        case 32 * 100 + 2 * 10 + A_DX3: return launch_one<32, 2, A_DX3>(dev, tm, a);
-        case 64 * 100 + 2 * 10 + A_DX3: return launch_one<64, 2, A_DX3>(dev, tm, a);
+        case 16 * 100 + 4 * 10 + 1: return launch_one<16, 4, true>(dev, tm, a);
+        case 32 * 100 + 4 * 10 + 1: return launch_one<32, 4, true>(dev, tm, a);
+        case 32 * 100 + 8 * 10 + 1: return launch_one<32, 8, true>(dev, tm, a);
+        case 48 * 100 + 4 * 10 + 1: return launch_one<48, 4, true>(dev, tm, a);
+        case 64 * 100 + 4 * 10 + 1: return launch_one<64, 4, true>(dev, tm, a);
+        case 32 * 100 + 4 * 10 + 0: return launch_one<32, 4, false>(dev, tm, a);
+        case 64 * 100 + 4 * 10 + 0: return launch_one<64, 4, false>(dev, tm, a);
         default:
             set_error(dev.err, "run_conv: no kernel instantiation for N=" + std::to_string(w.npad) +
-                                   " rows=" + std::to_string(rows) + " a_mode=" + std::to_string(c.a_mode));
+                                   " rows=" + std::to_string(rows) + " collector=" + std::to_string(coll));
             return -1;
     }
 }

@@ -119,39 +119,41 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool bf16 = 
 // ----------------------------------------------------------------------------------------------
 enum CollectorA { kCollNone = 0, kCollFill = 1, kCollUse = 2, kCollLastUse = 3 };
 
+// hi word of a K-major SWIZZLE_64B descriptor with SBO = 512 B (8 rows x 64 B): constant for the whole kernel.
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; descriptors passed as (lo, hi) words so that advancing a tile is one 32-bit add.
+#define VR_UMMA_ASM(MOD)                                                                                    \
+    asm volatile(                                                                                           \
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"                            \
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"                                               \
+        "tcgen05.mma.cta_group::1.kind::f16" MOD " [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),               \
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)                             \
+        : "memory")
+
 template <int kColl>
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
     if constexpr (kColl == kCollFill) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        VR_UMMA_ASM(".collector::a::fill");
     } else if constexpr (kColl == kCollUse) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}\n"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        VR_UMMA_ASM(".collector::a::use");
     } else if constexpr (kColl == kCollLastUse) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        VR_UMMA_ASM(".collector::a::lastuse");
     } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        VR_UMMA_ASM("");
     }
 }
-__device__ __forceinline__ void umma_f16_rt(int coll, uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
-                                            uint32_t acc) {
-    switch (coll) {
-        case kCollFill: umma_f16<kCollFill>(d, a, b, idesc, acc); break;
-        case kCollUse: umma_f16<kCollUse>(d, a, b, idesc, acc); break;
-        case kCollLastUse: umma_f16<kCollLastUse>(d, a, b, idesc, acc); break;
-        default: umma_f16<kCollNone>(d, a, b, idesc, acc); break;
-    }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    umma_f16<kCollNone>(d_tmem, static_cast<uint32_t>(adesc), static_cast<uint32_t>(adesc >> 32),
+                        static_cast<uint32_t>(bdesc), static_cast<uint32_t>(bdesc >> 32), idesc, accumulate);
 }
 // All previously issued MMAs of this thread arrive (once) on the mbarrier when they retire.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

@@ -109,9 +109,8 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     c.out_mode = rgb4 ? OUT_RGB4 : (ps4 ? OUT_PS4 : OUT_NHWC);
     c.base = dx;
     c.base_cstride = cin_pad;
-    c.a_mode = t->a_mode;
     c.rows = t->rows;
-    c.use_collector = t->use_collector;
+    c.flags = t->flags;
 
     const int iters = t->iters > 0 ? t->iters : 1;
     cudaEvent_t e0, e1;
@@ -157,7 +156,7 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
 }
 
 extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t rows,
-                                int32_t use_collector, int32_t iters, float* ms_out) {
+                                int32_t flags, int32_t iters, float* ms_out) {
     ScopedDev sd(device);
     if (!sd.ok) return VR_E_NODEVICE;
     Device& dev = sd.dev;
@@ -188,7 +187,7 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
     c.out_cstride = out_c;
     c.out_mode = (cout == 3) ? OUT_RGB4 : OUT_NHWC;
     c.rows = rows;
-    c.use_collector = use_collector;
+    c.flags = flags;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);

@@ -53,9 +53,8 @@ struct ConvCall {
     int out_mode = 0;  // ConvOut
     const __half* base = nullptr;
     int base_cstride = 0;
-    int a_mode = 0;  // ConvAMode
-    int rows = 0;    // TH, 0 = default
-    int use_collector = 1;
+    int rows = 0;   // output rows per CTA tile (TH), 0 = default
+    int flags = 0;  // ConvFlags (debug ablations)
 };
 
 struct Device {
@@ -64,8 +63,8 @@ struct Device {
     cudaStream_t stream = nullptr;
     std::string* err = nullptr;
     int64_t launches = 0;
-    // tensor-map cache: (ptr, cstride, W, H, rows, a_mode)
-    std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
+    // tensor-map cache: (ptr, cstride, W, H, rows)
+    std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;
 };
 
 int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const float* prelu, int cin, int cout,
