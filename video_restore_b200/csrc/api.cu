@@ -1,0 +1,746 @@
+// C ABI of libvrb200.so: handle lifetime, weight loading, the network executors (RRDBNet / SRVGGNetCompact as
+// sequences of K1 launches over zero-copy NHWC buffers), RealESRGANer tiling, and the per-frame restore chain.
+// Interface being replaced: reference video_upscaler.py:328-338 (constructor) and :490-505 (_process_frame).
+#include "../../include/vrb200.h"
+#include "conv3x3_sm100.cuh"
+#include "vr_common.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+using namespace vr;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct TileRect {
+    int in_x0, in_x1, in_y0, in_y1, pad_x0, pad_x1, pad_y0, pad_y1, out_x0, out_x1, out_y0, out_y1;
+};
+
+// RealESRGANer.tile_process index arithmetic ([3P] realesrgan/utils.py), integers only.
+std::vector<TileRect> make_tile_grid(int H, int W, int tile, int pad, int scale, int* tiles_x_out = nullptr,
+                                     int* tiles_y_out = nullptr) {
+    std::vector<TileRect> v;
+    const int tiles_x = (W + tile - 1) / tile, tiles_y = (H + tile - 1) / tile;
+    if (tiles_x_out) *tiles_x_out = tiles_x;
+    if (tiles_y_out) *tiles_y_out = tiles_y;
+    for (int y = 0; y < tiles_y; ++y)
+        for (int x = 0; x < tiles_x; ++x) {
+            TileRect t;
+            const int ofs_x = x * tile, ofs_y = y * tile;
+            t.in_x0 = ofs_x;
+            t.in_x1 = std::min(ofs_x + tile, W);
+            t.in_y0 = ofs_y;
+            t.in_y1 = std::min(ofs_y + tile, H);
+            t.pad_x0 = std::max(t.in_x0 - pad, 0);
+            t.pad_x1 = std::min(t.in_x1 + pad, W);
+            t.pad_y0 = std::max(t.in_y0 - pad, 0);
+            t.pad_y1 = std::min(t.in_y1 + pad, H);
+            t.out_x0 = (t.in_x0 - t.pad_x0) * scale;
+            t.out_x1 = t.out_x0 + (t.in_x1 - t.in_x0) * scale;
+            t.out_y0 = (t.in_y0 - t.pad_y0) * scale;
+            t.out_y1 = t.out_y0 + (t.in_y1 - t.in_y0) * scale;
+            v.push_back(t);
+        }
+    return v;
+}
+
+struct RawTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct vr_handle {
+    vr_config cfg;
+    Device dev;
+    std::string err;
+    std::map<std::string, RawTensor> raw;
+    std::map<std::string, ConvWeights> layers;
+    bool committed = false;
+    // network activations (NHWC fp16), grown on demand
+    DevBuf in32, feat, trunk, rdb[3], up1_in, up1_out, up2_in, up2_out, hr_out, sv[2];
+    std::vector<DevBuf> tile_out;
+    // u8 frames
+    DevBuf lr_in, lr_dn, hr[2], prev_up, stage_in, stage_out;
+    bool has_prev = false;
+    int prev_h = 0, prev_w = 0;
+    DevBuf clahe_hist, clahe_lut, tile_table;
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_net;
+    size_t ev_used = 0;
+    float last_total_ms = 0.f, last_conv_ms = 0.f;
+    bool timing_valid = false;
+};
+
+namespace {
+
+int ensure(vr_handle* h, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return 0;
+    if (b.p) {
+        VR_CUDA_CHECK(cudaStreamSynchronize(h->dev.stream), h->dev.err);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+        h->dev.tmaps.clear();
+    }
+    bytes = (bytes + 255) / 256 * 256;
+    VR_CUDA_CHECK(cudaMalloc(&b.p, bytes), h->dev.err);
+    b.bytes = bytes;
+    return 0;
+}
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+int fail(vr_handle* h, int code, const std::string& msg) {
+    set_error(&h->err, msg);
+    return code;
+}
+
+const ConvWeights* layer(vr_handle* h, const std::string& name) {
+    auto it = h->layers.find(name);
+    return it == h->layers.end() ? nullptr : &it->second;
+}
+
+#define VR_TRY(expr)            \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc) return _rc;    \
+    } while (0)
+
+// -------------------------------------------------------------------------------------------------
+// conv helper
+// -------------------------------------------------------------------------------------------------
+struct Act {
+    __half* p;
+    int c;  // channels per pixel
+};
+int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act,
+         const __half* res1 = nullptr, int res1_c = 0, float s1 = 1.f, const __half* res2 = nullptr, int res2_c = 0,
+         float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr, int base_c = 0) {
+    const ConvWeights* w = layer(h, name);
+    if (!w) return fail(h, VR_E_STATE, "missing layer " + name);
+    ConvCall c;
+    c.in = in.p;
+    c.in_cstride = in.c;
+    c.H = nh;
+    c.W = nw;
+    c.w = w;
+    c.act = act;
+    c.slope = 0.2f;
+    c.out = out.p;
+    c.out_cstride = out.c;
+    c.out_coff = out_coff;
+    c.res1 = res1;
+    c.res1_cstride = res1_c;
+    c.s1 = s1;
+    c.res2 = res2;
+    c.res2_cstride = res2_c;
+    c.s2 = s2;
+    c.out_mode = out_mode;
+    c.base = base;
+    c.base_cstride = base_c;
+    return run_conv(h->dev, c);
+}
+
+// RRDBNet.forward on one (already pixel-unshuffled when scale == 2) tile of nh x nw network pixels.
+// Dense concat is zero-copy: each RDB owns one 192-channel NHWC buffer; conv_k reads the channel prefix
+// [0, 64 + 32(k-1)) and writes its 32 channels behind it; conv5 writes the next RDB's channels [0, 64).
+int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
+    const size_t px = static_cast<size_t>(nh) * nw;
+    VR_TRY(ensure(h, h->feat, px * 64 * 2));
+    VR_TRY(ensure(h, h->trunk, px * 64 * 2));
+    for (int i = 0; i < 3; ++i) VR_TRY(ensure(h, h->rdb[i], px * 192 * 2));
+    VR_TRY(ensure(h, h->up1_in, px * 4 * 64 * 2));
+    VR_TRY(ensure(h, h->up1_out, px * 4 * 64 * 2));
+    VR_TRY(ensure(h, h->up2_in, px * 16 * 64 * 2));
+    VR_TRY(ensure(h, h->up2_out, px * 16 * 64 * 2));
+    Act in32{static_cast<__half*>(h->in32.p), 32};
+    Act feat{static_cast<__half*>(h->feat.p), 64};
+    Act trunk{static_cast<__half*>(h->trunk.p), 64};
+    Act rdb[3] = {{static_cast<__half*>(h->rdb[0].p), 192},
+                  {static_cast<__half*>(h->rdb[1].p), 192},
+                  {static_cast<__half*>(h->rdb[2].p), 192}};
+    // conv_first twice: once into `feat` (trunk residual), once into the first RDB buffer's x slot (K = 32: cheap)
+    VR_TRY(conv(h, "conv_first", in32, nh, nw, feat, 0, ACT_NONE));
+    VR_TRY(conv(h, "conv_first", in32, nh, nw, rdb[0], 0, ACT_NONE));
+    for (int b = 0; b < h->cfg.num_block; ++b) {
+        for (int r = 0; r < 3; ++r) {
+            const std::string pre = "body." + std::to_string(b) + ".rdb" + std::to_string(r + 1) + ".conv";
+            Act X = rdb[r], Y = rdb[(r + 1) % 3];
+            for (int k = 1; k <= 4; ++k) VR_TRY(conv(h, pre + std::to_string(k), X, nh, nw, X, 64 + 32 * (k - 1), ACT_LRELU));
+            if (r < 2) {
+                VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f));  // x5*0.2 + x
+            } else {
+                // (x5*0.2 + x)*0.2 + rrdb_in ; rrdb_in lives in rdb[0][:, 0:64] and is overwritten in place
+                VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f, Y.p, 192, 0.2f));
+            }
+        }
+    }
+    VR_TRY(conv(h, "conv_body", rdb[0], nh, nw, trunk, 0, ACT_NONE, feat.p, 64, 1.0f));  // feat + body_feat
+    Act u1i{static_cast<__half*>(h->up1_in.p), 64}, u1o{static_cast<__half*>(h->up1_out.p), 64};
+    Act u2i{static_cast<__half*>(h->up2_in.p), 64}, u2o{static_cast<__half*>(h->up2_out.p), 64};
+    VR_TRY(launch_upsample2x(h->dev, trunk.p, nh, nw, 64, u1i.p));
+    VR_TRY(conv(h, "conv_up1", u1i, 2 * nh, 2 * nw, u1o, 0, ACT_LRELU));
+    VR_TRY(launch_upsample2x(h->dev, u1o.p, 2 * nh, 2 * nw, 64, u2i.p));
+    VR_TRY(conv(h, "conv_up2", u2i, 4 * nh, 4 * nw, u2o, 0, ACT_LRELU));
+    VR_TRY(conv(h, "conv_hr", u2o, 4 * nh, 4 * nw, u2i, 0, ACT_LRELU));  // up2_in is dead: reuse for conv_hr out
+    Act to{tile_out, 4};
+    VR_TRY(conv(h, "conv_last", u2i, 4 * nh, 4 * nw, to, 0, ACT_NONE, nullptr, 0, 1.f, nullptr, 0, 1.f, OUT_RGB4));
+    return 0;
+}
+
+// SRVGGNetCompact.forward: conv+PReLU chain, last conv fused with PixelShuffle(4) + nearest-upsampled input.
+int run_srvgg(vr_handle* h, int nh, int nw, __half* tile_out) {
+    const size_t px = static_cast<size_t>(nh) * nw;
+    VR_TRY(ensure(h, h->sv[0], px * 64 * 2));
+    VR_TRY(ensure(h, h->sv[1], px * 64 * 2));
+    Act in32{static_cast<__half*>(h->in32.p), 32};
+    Act a{static_cast<__half*>(h->sv[0].p), 64}, b{static_cast<__half*>(h->sv[1].p), 64};
+    VR_TRY(conv(h, "body.0", in32, nh, nw, a, 0, ACT_PRELU));
+    for (int i = 0; i < h->cfg.num_conv; ++i) {
+        VR_TRY(conv(h, "body." + std::to_string(2 * (i + 1)), a, nh, nw, b, 0, ACT_PRELU));
+        std::swap(a, b);
+    }
+    Act to{tile_out, 4};
+    VR_TRY(conv(h, "body." + std::to_string(2 * (h->cfg.num_conv + 1)), a, nh, nw, to, 0, ACT_NONE, nullptr, 0, 1.f,
+                nullptr, 0, 1.f, OUT_PS4, in32.p, 32));
+    return 0;
+}
+
+cudaEvent_t next_event(vr_handle* h) {
+    if (h->ev_used == h->ev_net.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_net.push_back(e);
+    }
+    return h->ev_net[h->ev_used++];
+}
+
+// The whole per-frame chain on device-resident frames; enqueues on h->dev.stream, no host sync on the way
+// (except first-use allocations).
+int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t stride, uint8_t* d_out,
+                    int64_t out_stride, const vr_frame_opts* opts) {
+    if (!h->committed) return fail(h, VR_E_STATE, "vr_restore before vr_commit_weights");
+    if (H <= 0 || W <= 0 || !d_bgr || !d_out) return fail(h, VR_E_INVALID, "vr_restore: bad frame arguments");
+    vr_frame_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    const vr_config& cfg = h->cfg;
+    const int s = cfg.scale;
+    const int sH = H * s, sW = W * s;
+    Device& dev = h->dev;
+    VR_CUDA_CHECK(cudaSetDevice(dev.ordinal), dev.err);
+    h->ev_used = 0;
+    cudaEventRecord(h->ev_total[0], dev.stream);
+
+    // (1) bilateral pre-denoise on the LR frame (video_upscaler.py:495-496)
+    const uint8_t* src = d_bgr;
+    int64_t sstride = stride;
+    if (o.denoise) {
+        VR_TRY(ensure(h, h->lr_dn, static_cast<size_t>(H) * W * 3));
+        VR_TRY(launch_bilateral(dev, src, sstride, H, W, static_cast<uint8_t*>(h->lr_dn.p), static_cast<int64_t>(W) * 3,
+                                o.denoise_d, o.denoise_sigma_color, o.denoise_sigma_space));
+        src = static_cast<const uint8_t*>(h->lr_dn.p);
+        sstride = static_cast<int64_t>(W) * 3;
+    }
+
+    // (2) RealESRGANer.enhance: mod-pad (scale 2), tile loop, merge
+    int Hp = H, Wp = W;
+    if (s == 2) {
+        Hp += H % 2;
+        Wp += W % 2;
+    }
+    int tiles_x = 0, tiles_y = 0;
+    const std::vector<TileRect> grid = make_tile_grid(Hp, Wp, cfg.tile, cfg.tile_pad, s, &tiles_x, &tiles_y);
+    const bool post_chain = (o.sharpen > 0.f) || o.clahe || o.temporal;
+    const size_t hr_bytes = static_cast<size_t>(sH) * sW * 3;
+    const int64_t hr_stride = static_cast<int64_t>(sW) * 3;
+    uint8_t* up_dst = d_out;
+    int64_t up_stride = out_stride;
+    if (post_chain) {
+        VR_TRY(ensure(h, h->hr[0], hr_bytes));
+        up_dst = static_cast<uint8_t*>(h->hr[0].p);
+        up_stride = hr_stride;
+    }
+    const bool blend = cfg.blend == VR_BLEND_GAUSSIAN;
+    if (h->tile_out.size() < (blend ? grid.size() : 1)) h->tile_out.resize(blend ? grid.size() : 1);
+    std::vector<BlendTile> btiles;
+    for (size_t ti = 0; ti < grid.size(); ++ti) {
+        const TileRect& t = grid[ti];
+        const int pw = t.pad_x1 - t.pad_x0, ph = t.pad_y1 - t.pad_y0;
+        if (s == 2 && ((pw | ph) & 1))
+            return fail(h, VR_E_INVALID,
+                        "x2 model: padded tile extent must be even (pixel_unshuffle); use an even tile size/overlap");
+        const int nh = s == 2 ? ph / 2 : ph, nw = s == 2 ? pw / 2 : pw;
+        VR_TRY(ensure(h, h->in32, static_cast<size_t>(nh) * nw * 32 * 2));
+        DevBuf& tob = h->tile_out[blend ? ti : 0];
+        VR_TRY(ensure(h, tob, static_cast<size_t>(ph) * s * pw * s * 4 * 2));
+        VR_TRY(launch_pre(dev, src, sstride, H, W, t.pad_x0, t.pad_y0, pw, ph, s == 2 ? 1 : 0,
+                          static_cast<__half*>(h->in32.p)));
+        cudaEventRecord(next_event(h), dev.stream);
+        if (cfg.model_kind == VR_MODEL_RRDBNET)
+            VR_TRY(run_rrdbnet(h, nh, nw, static_cast<__half*>(tob.p)));
+        else
+            VR_TRY(run_srvgg(h, nh, nw, static_cast<__half*>(tob.p)));
+        cudaEventRecord(next_event(h), dev.stream);
+        if (blend) {
+            btiles.push_back({static_cast<const __half*>(tob.p), t.pad_x0 * s, t.pad_y0 * s, pw * s, ph * s});
+        } else {
+            const int dx0 = t.in_x0 * s, dy0 = t.in_y0 * s;
+            const int w = std::min(t.in_x1 * s, sW) - dx0, hh = std::min(t.in_y1 * s, sH) - dy0;  // un-pad (post_process)
+            VR_TRY(launch_post_crop(dev, static_cast<const __half*>(tob.p), pw * s, t.out_x0, t.out_y0, w, hh, up_dst,
+                                    up_stride, dx0, dy0));
+        }
+    }
+    if (blend) {
+        VR_TRY(ensure(h, h->tile_table, grid.size() * 32));
+        VR_TRY(launch_post_blend(dev, btiles, tiles_x, tiles_y, cfg.tile * s, cfg.tile_pad * s, up_dst, up_stride, sH,
+                                 sW, h->tile_table.p));
+    }
+
+    // (3) enhancement stage on the HR u8 frame; the last stage writes straight into d_out
+    if (post_chain) {
+        int cur = 0;  // h->hr[cur] holds the current frame
+        auto cur_ptr = [&]() { return static_cast<uint8_t*>(h->hr[cur].p); };
+        const bool has_sharpen = o.sharpen > 0.f;
+        if (has_sharpen) {
+            const bool last = !o.clahe && !o.temporal;
+            uint8_t* dst = d_out;
+            int64_t dstride = out_stride;
+            if (!last) {
+                VR_TRY(ensure(h, h->hr[cur ^ 1], hr_bytes));
+                dst = static_cast<uint8_t*>(h->hr[cur ^ 1].p);
+                dstride = hr_stride;
+            }
+            VR_TRY(launch_unsharp(dev, cur_ptr(), hr_stride, sH, sW, dst, dstride, o.sharpen));
+            if (!last) cur ^= 1;
+        }
+        if (o.clahe) {
+            const bool last = !o.temporal;
+            uint8_t* dst = d_out;
+            int64_t dstride = out_stride;
+            if (!last) {
+                VR_TRY(ensure(h, h->hr[cur ^ 1], hr_bytes));
+                dst = static_cast<uint8_t*>(h->hr[cur ^ 1].p);
+                dstride = hr_stride;
+            }
+            const int g = o.clahe_grid > 0 ? o.clahe_grid : 8;
+            VR_TRY(ensure(h, h->clahe_hist, static_cast<size_t>(g) * g * 256 * 4));
+            VR_TRY(ensure(h, h->clahe_lut, static_cast<size_t>(g) * g * 256));
+            VR_TRY(launch_clahe(dev, cur_ptr(), hr_stride, sH, sW, dst, dstride, o.clahe_clip > 0 ? o.clahe_clip : 2.0f, g,
+                                static_cast<int32_t*>(h->clahe_hist.p), static_cast<uint8_t*>(h->clahe_lut.p), nullptr));
+            if (!last) cur ^= 1;
+        }
+        if (o.temporal) {
+            const float alpha = o.temporal_alpha > 0 ? o.temporal_alpha : 0.2f;
+            const float tau = o.temporal_tau > 0 ? o.temporal_tau : 12.f;
+            if (h->has_prev && h->prev_h == sH && h->prev_w == sW) {
+                VR_TRY(launch_temporal(dev, cur_ptr(), hr_stride, static_cast<const uint8_t*>(h->prev_up.p), hr_stride,
+                                       sH, sW, d_out, out_stride, alpha, tau));
+            } else {
+                VR_CUDA_CHECK(cudaMemcpy2DAsync(d_out, out_stride, cur_ptr(), hr_stride, hr_stride, sH,
+                                                cudaMemcpyDeviceToDevice, dev.stream),
+                              dev.err);
+            }
+            std::swap(h->hr[cur], h->prev_up);  // up_t becomes up_{t-1}; no copy
+            h->has_prev = true;
+            h->prev_h = sH;
+            h->prev_w = sW;
+        }
+    }
+    cudaEventRecord(h->ev_total[1], dev.stream);
+    h->timing_valid = false;
+    return 0;
+}
+
+int finish_timing(vr_handle* h) {
+    VR_CUDA_CHECK(cudaStreamSynchronize(h->dev.stream), h->dev.err);
+    cudaEventElapsedTime(&h->last_total_ms, h->ev_total[0], h->ev_total[1]);
+    float conv = 0.f;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_net[i], h->ev_net[i + 1]);
+        conv += ms;
+    }
+    h->last_conv_ms = conv;
+    h->timing_valid = true;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported ABI
+// =================================================================================================
+extern "C" {
+
+int vr_create(const vr_config* cfg, vr_handle** out) {
+    if (!cfg || !out) {
+        g_create_error = "vr_create: null argument";
+        set_error(nullptr, g_create_error);
+        return VR_E_INVALID;
+    }
+    auto bad = [&](const std::string& m, int code) {
+        g_create_error = m;
+        set_error(nullptr, m);
+        return code;
+    };
+    if (cfg->model_kind != VR_MODEL_RRDBNET && cfg->model_kind != VR_MODEL_SRVGG)
+        return bad("vr_create: unknown model_kind", VR_E_INVALID);
+    if (cfg->model_kind == VR_MODEL_RRDBNET && cfg->scale != 4 && cfg->scale != 2)
+        return bad("vr_create: RRDBNet scale must be 4 or 2", VR_E_INVALID);
+    if (cfg->model_kind == VR_MODEL_SRVGG && cfg->scale != 4) return bad("vr_create: SRVGG scale must be 4", VR_E_INVALID);
+    if (cfg->num_feat != 64 || (cfg->model_kind == VR_MODEL_RRDBNET && cfg->num_grow_ch != 32))
+        return bad("vr_create: only num_feat=64 / num_grow_ch=32 (the reference's architectures) are built", VR_E_INVALID);
+    if (cfg->tile <= 0 || cfg->tile_pad < 0) return bad("vr_create: tile must be > 0 and tile_pad >= 0", VR_E_INVALID);
+    if (cfg->pre_pad != 0) return bad("vr_create: pre_pad != 0 is not supported (reference passes 0)", VR_E_INVALID);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return bad("vr_create: no CUDA device (this library has no CPU fallback)", VR_E_NODEVICE);
+    if (cfg->device < 0 || cfg->device >= ndev) return bad("vr_create: device ordinal out of range", VR_E_NODEVICE);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, cfg->device) != cudaSuccess) return bad("cudaGetDeviceProperties failed", VR_E_CUDA);
+    if (p.major != 10)
+        return bad("vr_create: device is sm_" + std::to_string(p.major * 10 + p.minor) +
+                       ", this library is built for sm_100a only",
+                   VR_E_NODEVICE);
+    std::unique_ptr<vr_handle> h(new vr_handle());
+    h->cfg = *cfg;
+    h->dev.ordinal = cfg->device;
+    h->dev.sm_count = p.multiProcessorCount;
+    h->dev.err = &h->err;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);
+    if (cudaStreamCreateWithFlags(&h->dev.stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bad("cudaStreamCreate failed", VR_E_CUDA);
+    cudaEventCreate(&h->ev_total[0]);
+    cudaEventCreate(&h->ev_total[1]);
+    *out = h.release();
+    return VR_OK;
+}
+
+void vr_destroy(vr_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->dev.ordinal);
+    if (h->dev.stream) cudaStreamSynchronize(h->dev.stream);
+    for (auto& kv : h->layers) free_conv_weights(&kv.second);
+    DevBuf* bufs[] = {&h->in32, &h->feat, &h->trunk, &h->rdb[0], &h->rdb[1], &h->rdb[2], &h->up1_in, &h->up1_out,
+                      &h->up2_in, &h->up2_out, &h->hr_out, &h->sv[0], &h->sv[1], &h->lr_in, &h->lr_dn, &h->hr[0],
+                      &h->hr[1], &h->prev_up, &h->stage_in, &h->stage_out, &h->clahe_hist, &h->clahe_lut,
+                      &h->tile_table};
+    for (DevBuf* b : bufs) release(*b);
+    for (auto& b : h->tile_out) release(b);
+    for (auto e : h->ev_net) cudaEventDestroy(e);
+    if (h->ev_total[0]) cudaEventDestroy(h->ev_total[0]);
+    if (h->ev_total[1]) cudaEventDestroy(h->ev_total[1]);
+    if (h->dev.stream) cudaStreamDestroy(h->dev.stream);
+    delete h;
+}
+
+const char* vr_last_error(const vr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vr_load_tensor(vr_handle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+    if (!h) return VR_E_INVALID;
+    if (!name || !data || !shape || ndim < 1 || ndim > 4) return fail(h, VR_E_INVALID, "vr_load_tensor: bad arguments");
+    RawTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0) return fail(h, VR_E_INVALID, "vr_load_tensor: non-positive dimension");
+        t.shape.push_back(shape[i]);
+        n *= static_cast<size_t>(shape[i]);
+    }
+    t.data.assign(data, data + n);
+    h->raw[name] = std::move(t);
+    h->committed = false;
+    return VR_OK;
+}
+
+int vr_commit_weights(vr_handle* h) {
+    if (!h) return VR_E_INVALID;
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    for (auto& kv : h->layers) free_conv_weights(&kv.second);
+    h->layers.clear();
+    // expected layer list: (prefix, cin, cout, prelu key or "")
+    struct Spec {
+        std::string name;
+        int cin, cout;
+        std::string prelu;
+    };
+    std::vector<Spec> specs;
+    const vr_config& c = h->cfg;
+    if (c.model_kind == VR_MODEL_RRDBNET) {
+        specs.push_back({"conv_first", c.scale == 2 ? 12 : 3, 64, ""});
+        for (int b = 0; b < c.num_block; ++b)
+            for (int r = 1; r <= 3; ++r)
+                for (int k = 1; k <= 5; ++k)
+                    specs.push_back({"body." + std::to_string(b) + ".rdb" + std::to_string(r) + ".conv" + std::to_string(k),
+                                     64 + 32 * (k - 1), k < 5 ? 32 : 64, ""});
+        for (const char* n : {"conv_body", "conv_up1", "conv_up2", "conv_hr"}) specs.push_back({n, 64, 64, ""});
+        specs.push_back({"conv_last", 64, 3, ""});
+    } else {
+        specs.push_back({"body.0", 3, 64, "body.1.weight"});
+        for (int i = 0; i < c.num_conv; ++i)
+            specs.push_back({"body." + std::to_string(2 * (i + 1)), 64, 64, "body." + std::to_string(2 * (i + 1) + 1) + ".weight"});
+        specs.push_back({"body." + std::to_string(2 * (c.num_conv + 1)), 64, 48, ""});
+    }
+    for (const Spec& s : specs) {
+        auto wi = h->raw.find(s.name + ".weight");
+        auto bi = h->raw.find(s.name + ".bias");
+        if (wi == h->raw.end() || bi == h->raw.end()) return fail(h, VR_E_STATE, "missing tensor " + s.name + ".weight/.bias");
+        const RawTensor& w = wi->second;
+        if (w.shape.size() != 4 || w.shape[0] != s.cout || w.shape[1] != s.cin || w.shape[2] != 3 || w.shape[3] != 3)
+            return fail(h, VR_E_INVALID, "tensor " + s.name + ".weight has the wrong shape");
+        if (bi->second.data.size() != static_cast<size_t>(s.cout))
+            return fail(h, VR_E_INVALID, "tensor " + s.name + ".bias has the wrong shape");
+        const float* prelu = nullptr;
+        if (!s.prelu.empty()) {
+            auto pi = h->raw.find(s.prelu);
+            if (pi == h->raw.end() || pi->second.data.size() != static_cast<size_t>(s.cout))
+                return fail(h, VR_E_STATE, "missing/ill-shaped PReLU tensor " + s.prelu);
+            prelu = pi->second.data.data();
+        }
+        ConvWeights cw;
+        VR_TRY(pack_conv_weights(h->dev, w.data.data(), bi->second.data.data(), prelu, s.cin, s.cout, &cw));
+        h->layers[s.name] = cw;
+    }
+    h->raw.clear();
+    h->committed = true;
+    return VR_OK;
+}
+
+int vr_restore_device_async(vr_handle* h, const uint8_t* d_bgr, int32_t H, int32_t W, int64_t stride, uint8_t* d_out,
+                            int64_t out_stride, const vr_frame_opts* opts) {
+    if (!h) return VR_E_INVALID;
+    return restore_enqueue(h, d_bgr, H, W, stride, d_out, out_stride, opts);
+}
+
+int vr_sync(vr_handle* h) {
+    if (!h) return VR_E_INVALID;
+    return finish_timing(h);
+}
+
+void* vr_stream(vr_handle* h) { return h ? static_cast<void*>(h->dev.stream) : nullptr; }
+
+int vr_restore_device(vr_handle* h, const uint8_t* d_bgr, int32_t H, int32_t W, int64_t stride, uint8_t* d_out,
+                      int64_t out_stride, const vr_frame_opts* opts) {
+    if (!h) return VR_E_INVALID;
+    VR_TRY(restore_enqueue(h, d_bgr, H, W, stride, d_out, out_stride, opts));
+    return finish_timing(h);
+}
+
+int vr_restore(vr_handle* h, const uint8_t* bgr, int32_t H, int32_t W, int64_t stride, uint8_t* out,
+               int64_t out_stride, const vr_frame_opts* opts) {
+    if (!h) return VR_E_INVALID;
+    if (!bgr || !out || H <= 0 || W <= 0) return fail(h, VR_E_INVALID, "vr_restore: bad frame arguments");
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    const int s = h->cfg.scale;
+    const size_t in_row = static_cast<size_t>(W) * 3, out_row = static_cast<size_t>(W) * s * 3;
+    VR_TRY(ensure(h, h->stage_in, in_row * H));
+    VR_TRY(ensure(h, h->stage_out, out_row * H * s));
+    VR_CUDA_CHECK(cudaMemcpy2DAsync(h->stage_in.p, in_row, bgr, stride, in_row, H, cudaMemcpyHostToDevice, h->dev.stream),
+                  h->dev.err);
+    VR_TRY(restore_enqueue(h, static_cast<const uint8_t*>(h->stage_in.p), H, W, in_row,
+                           static_cast<uint8_t*>(h->stage_out.p), out_row, opts));
+    VR_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, h->stage_out.p, out_row, out_row, static_cast<size_t>(H) * s,
+                                    cudaMemcpyDeviceToHost, h->dev.stream),
+                  h->dev.err);
+    return finish_timing(h);
+}
+
+int vr_temporal_reset(vr_handle* h) {
+    if (!h) return VR_E_INVALID;
+    h->has_prev = false;
+    return VR_OK;
+}
+
+int vr_temporal_set_prev(vr_handle* h, const uint8_t* up_prev, int32_t sH, int32_t sW, int64_t stride, int32_t is_device) {
+    if (!h || !up_prev || sH <= 0 || sW <= 0) return VR_E_INVALID;
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    const size_t row = static_cast<size_t>(sW) * 3;
+    VR_TRY(ensure(h, h->prev_up, row * sH));
+    VR_CUDA_CHECK(cudaMemcpy2DAsync(h->prev_up.p, row, up_prev, stride, row, sH,
+                                    is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->dev.stream),
+                  h->dev.err);
+    VR_CUDA_CHECK(cudaStreamSynchronize(h->dev.stream), h->dev.err);
+    h->has_prev = true;
+    h->prev_h = sH;
+    h->prev_w = sW;
+    return VR_OK;
+}
+
+int vr_temporal_get_prev(vr_handle* h, uint8_t* dst, int32_t sH, int32_t sW, int64_t stride, int32_t is_device) {
+    if (!h || !dst) return VR_E_INVALID;
+    if (!h->has_prev || h->prev_h != sH || h->prev_w != sW) return fail(h, VR_E_STATE, "no previous frame of that size");
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    const size_t row = static_cast<size_t>(sW) * 3;
+    VR_CUDA_CHECK(cudaMemcpy2DAsync(dst, stride, h->prev_up.p, row, row, sH,
+                                    is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->dev.stream),
+                  h->dev.err);
+    VR_CUDA_CHECK(cudaStreamSynchronize(h->dev.stream), h->dev.err);
+    return VR_OK;
+}
+
+int vr_tile_grid(int32_t H, int32_t W, int32_t tile, int32_t tile_pad, int32_t scale, int32_t* table,
+                 int32_t max_tiles) {
+    if (H <= 0 || W <= 0 || tile <= 0 || tile_pad < 0 || scale <= 0) return VR_E_INVALID;
+    const std::vector<TileRect> g = make_tile_grid(H, W, tile, tile_pad, scale);
+    if (table) {
+        const int n = std::min<int>(static_cast<int>(g.size()), max_tiles);
+        for (int i = 0; i < n; ++i) std::memcpy(table + i * 12, &g[i], 12 * sizeof(int32_t));
+    }
+    return static_cast<int>(g.size());
+}
+
+int64_t vr_launch_count(const vr_handle* h) { return h ? h->dev.launches : 0; }
+
+int vr_last_timing(const vr_handle* h, float* total_ms, float* conv_ms) {
+    if (!h || !h->timing_valid) return VR_E_STATE;
+    if (total_ms) *total_ms = h->last_total_ms;
+    if (conv_ms) *conv_ms = h->last_conv_ms;
+    return VR_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// stand-alone filter entry points (host buffers): thin staging around the same kernels
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct TmpDev {
+    Device dev;
+    std::string err;
+    bool ok = false;
+    explicit TmpDev(int ordinal) {
+        dev.err = &err;
+        dev.ordinal = ordinal;
+        cudaDeviceProp p;
+        if (cudaSetDevice(ordinal) != cudaSuccess || cudaGetDeviceProperties(&p, ordinal) != cudaSuccess) {
+            set_error(&err, "no usable CUDA device (this library has no CPU fallback)");
+            return;
+        }
+        dev.sm_count = p.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error(&err, "cudaStreamCreate failed");
+            return;
+        }
+        ok = true;
+    }
+    ~TmpDev() {
+        if (dev.stream) cudaStreamDestroy(dev.stream);
+    }
+};
+template <typename F>
+int run_filter(int device, const uint8_t* src, const uint8_t* src2, int H, int W, uint8_t* dst, F&& f) {
+    if (!src || !dst || H <= 0 || W <= 0) {
+        set_error(nullptr, "filter: bad arguments");
+        return VR_E_INVALID;
+    }
+    TmpDev td(device);
+    if (!td.ok) return VR_E_NODEVICE;
+    const size_t bytes = static_cast<size_t>(H) * W * 3;
+    uint8_t *d_src = nullptr, *d_src2 = nullptr, *d_dst = nullptr;
+    VR_CUDA_CHECK(cudaMalloc(&d_src, bytes), td.dev.err);
+    VR_CUDA_CHECK(cudaMalloc(&d_dst, bytes), td.dev.err);
+    VR_CUDA_CHECK(cudaMemcpy(d_src, src, bytes, cudaMemcpyHostToDevice), td.dev.err);
+    if (src2) {
+        VR_CUDA_CHECK(cudaMalloc(&d_src2, bytes), td.dev.err);
+        VR_CUDA_CHECK(cudaMemcpy(d_src2, src2, bytes, cudaMemcpyHostToDevice), td.dev.err);
+    }
+    int rc = f(td.dev, d_src, d_src2, d_dst);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(td.dev.stream);
+        if (e != cudaSuccess) {
+            set_error(td.dev.err, std::string("filter kernel failed: ") + cudaGetErrorString(e));
+            rc = VR_E_CUDA;
+        } else {
+            cudaMemcpy(dst, d_dst, bytes, cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFree(d_src);
+    cudaFree(d_dst);
+    if (d_src2) cudaFree(d_src2);
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int vr_bilateral(int32_t device, const uint8_t* src, int32_t H, int32_t W, uint8_t* dst, int32_t d, float sigma_color,
+                 float sigma_space) {
+    const int64_t st = static_cast<int64_t>(W) * 3;
+    return run_filter(device, src, nullptr, H, W, dst, [&](Device& dev, uint8_t* s, uint8_t*, uint8_t* o) {
+        return launch_bilateral(dev, s, st, H, W, o, st, d, sigma_color, sigma_space);
+    });
+}
+
+int vr_unsharp(int32_t device, const uint8_t* src, int32_t H, int32_t W, uint8_t* dst, float amount) {
+    const int64_t st = static_cast<int64_t>(W) * 3;
+    return run_filter(device, src, nullptr, H, W, dst, [&](Device& dev, uint8_t* s, uint8_t*, uint8_t* o) {
+        return launch_unsharp(dev, s, st, H, W, o, st, amount);
+    });
+}
+
+int vr_clahe(int32_t device, const uint8_t* src, int32_t H, int32_t W, uint8_t* dst, float clip, int32_t grid,
+             int32_t* hist_out, uint8_t* lut_out) {
+    const int64_t st = static_cast<int64_t>(W) * 3;
+    return run_filter(device, src, nullptr, H, W, dst, [&](Device& dev, uint8_t* s, uint8_t*, uint8_t* o) {
+        int32_t* d_hist = nullptr;
+        uint8_t* d_lut = nullptr;
+        const size_t n = static_cast<size_t>(grid) * grid * 256;
+        if (grid < 1 || grid > 16) {
+            set_error(dev.err, "clahe: grid must be 1..16");
+            return VR_E_INVALID;
+        }
+        VR_CUDA_CHECK(cudaMalloc(&d_hist, n * 4), dev.err);
+        VR_CUDA_CHECK(cudaMalloc(&d_lut, n), dev.err);
+        int rc = launch_clahe(dev, s, st, H, W, o, st, clip, grid, d_hist, d_lut, nullptr);
+        if (rc == 0 && cudaStreamSynchronize(dev.stream) == cudaSuccess) {
+            if (hist_out) cudaMemcpy(hist_out, d_hist, n * 4, cudaMemcpyDeviceToHost);
+            if (lut_out) cudaMemcpy(lut_out, d_lut, n, cudaMemcpyDeviceToHost);
+        }
+        cudaFree(d_hist);
+        cudaFree(d_lut);
+        return rc;
+    });
+}
+
+int vr_temporal(int32_t device, const uint8_t* cur, const uint8_t* prev, int32_t H, int32_t W, uint8_t* dst,
+                float alpha, float tau) {
+    if (!prev) {
+        set_error(nullptr, "vr_temporal: prev is null");
+        return VR_E_INVALID;
+    }
+    const int64_t st = static_cast<int64_t>(W) * 3;
+    return run_filter(device, cur, prev, H, W, dst, [&](Device& dev, uint8_t* s, uint8_t* p, uint8_t* o) {
+        return launch_temporal(dev, s, st, p, st, H, W, o, st, alpha, tau);
+    });
+}
+
+int vr_blend_weights(int32_t device, int32_t extent, float* w_out) {
+    if (extent <= 0 || !w_out) return VR_E_INVALID;
+    TmpDev td(device);
+    if (!td.ok) return VR_E_NODEVICE;
+    float* d = nullptr;
+    VR_CUDA_CHECK(cudaMalloc(&d, extent * sizeof(float)), td.dev.err);
+    int rc = launch_blend_weights(td.dev, extent, d);
+    if (rc == 0) {
+        if (cudaStreamSynchronize(td.dev.stream) != cudaSuccess) rc = VR_E_CUDA;
+        else cudaMemcpy(w_out, d, extent * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

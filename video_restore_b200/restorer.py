@@ -1,0 +1,257 @@
+"""Host-side mirror of the reference's per-frame interface, over the C ABI of libvrb200.so.
+
+`RealESRGANer` keeps the constructor and `enhance(img, outscale) -> (uint8 BGR, 'RGB')` contract the reference
+uses (video_upscaler.py:328-338, :501); `FrameRestorer` is `_process_frame` (video_upscaler.py:490-505) plus the
+README-only enhancement stage. All arithmetic happens in hand-written sm_100a kernels; this file only moves
+pointers. There is no CPU fallback: construction raises VrError without a B200 and the built library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import VrConfig, VrError, VrFrameOpts
+from .models import MODEL_ZOO
+
+
+@dataclass
+class FrameOpts:
+    """Per-frame enhancement switches; defaults == plain `enhance`."""
+    denoise: bool = False          # bilateral 5/25/25 on the LR frame, video_upscaler.py:495-496
+    denoise_d: int = 5
+    denoise_sigma_color: float = 25.0
+    denoise_sigma_space: float = 25.0
+    sharpen: float = 0.0           # unsharp amount, README.md:141
+    clahe: bool = False            # README.md:11,240
+    clahe_clip: float = 2.0
+    clahe_grid: int = 8
+    temporal: bool = False         # README.md:9,237
+    temporal_alpha: float = 0.2
+    temporal_tau: float = 12.0
+
+    def to_c(self) -> VrFrameOpts:
+        return VrFrameOpts(denoise=int(self.denoise), denoise_d=self.denoise_d,
+                           denoise_sigma_color=self.denoise_sigma_color, denoise_sigma_space=self.denoise_sigma_space,
+                           sharpen=self.sharpen, clahe=int(self.clahe), clahe_clip=self.clahe_clip,
+                           clahe_grid=self.clahe_grid, temporal=int(self.temporal),
+                           temporal_alpha=self.temporal_alpha, temporal_tau=self.temporal_tau)
+
+
+def _as_spec(model):
+    if isinstance(model, str):
+        if model not in MODEL_ZOO:
+            raise ValueError(f"Unsupported model: {model}")  # same message as video_upscaler.py:323
+        return dict(MODEL_ZOO[model])
+    if isinstance(model, dict):
+        return dict(model)
+    raise TypeError("model must be a model-zoo name or a spec dict(kind, scale, num_block, num_conv)")
+
+
+class FrameRestorer:
+    """One instance per (GPU, host thread), like `self.models[gpu_id]` in the reference (video_upscaler.py:340)."""
+
+    def __init__(self, model="RealESRGAN_x4plus", state_dict=None, tile=512, tile_pad=10, pre_pad=0,
+                 blend="crop", gpu_id=0):
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        spec = _as_spec(model)
+        self.spec = spec
+        self.scale = spec["scale"]
+        cfg = VrConfig(model_kind=_lib.VR_MODEL_RRDBNET if spec["kind"] == "rrdb" else _lib.VR_MODEL_SRVGG,
+                       scale=spec["scale"], num_block=spec.get("num_block", 0), num_conv=spec.get("num_conv", 0),
+                       num_feat=64, num_grow_ch=32, tile=int(tile), tile_pad=int(tile_pad), pre_pad=int(pre_pad),
+                       blend=_lib.VR_BLEND_GAUSSIAN if blend == "gaussian" else _lib.VR_BLEND_CROP,
+                       device=int(gpu_id))
+        rc = self._lib.vr_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise VrError(f"vr_create failed ({rc}): {(self._lib.vr_last_error(None) or b'').decode()}")
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # -- weights ---------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict) -> None:
+        """`state_dict`: mapping upstream key -> array-like float (torch tensors or numpy), as in a .pth's
+        params_ema / params."""
+        for name, t in state_dict.items():
+            a = np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t, dtype=np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            _lib.check(self._lib.vr_load_tensor(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim),
+                       self._h)
+        _lib.check(self._lib.vr_commit_weights(self._h), self._h)
+
+    # -- the hot path ----------------------------------------------------------------------------
+    def process_frame(self, frame: np.ndarray, opts: FrameOpts | None = None, out: np.ndarray | None = None):
+        """uint8 [H,W,3] BGR (read-only is fine) -> freshly allocated uint8 [sH,sW,3] BGR."""
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be uint8 HxWx3 BGR")
+        if frame.strides[2] != 1 or frame.strides[1] != 3:
+            frame = np.ascontiguousarray(frame)
+        H, W, _ = frame.shape
+        s = self.scale
+        if out is None:
+            out = np.empty((H * s, W * s, 3), np.uint8)
+        o = (opts or FrameOpts()).to_c()
+        rc = self._lib.vr_restore(self._h, frame.ctypes.data_as(C.c_void_p), H, W, frame.strides[0],
+                                  out.ctypes.data_as(C.c_void_p), out.strides[0], C.byref(o))
+        _lib.check(rc, self._h)
+        return out
+
+    def process_frame_device(self, d_in: int, H: int, W: int, d_out: int, opts: FrameOpts | None = None,
+                             sync: bool = True) -> None:
+        """Device-resident frames (raw pointers on this restorer's GPU), dense rows."""
+        o = (opts or FrameOpts()).to_c()
+        fn = self._lib.vr_restore_device if sync else self._lib.vr_restore_device_async
+        _lib.check(fn(self._h, C.c_void_p(d_in), H, W, W * 3, C.c_void_p(d_out), W * self.scale * 3, C.byref(o)),
+                   self._h)
+
+    def sync(self) -> None:
+        _lib.check(self._lib.vr_sync(self._h), self._h)
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.vr_stream(self._h) or 0)
+
+    # -- temporal state (frame-range sharding hands the boundary frame across) ----------------------
+    def temporal_reset(self) -> None:
+        _lib.check(self._lib.vr_temporal_reset(self._h), self._h)
+
+    def temporal_set_prev(self, up_prev, device_ptr: bool = False, shape=None) -> None:
+        if device_ptr:
+            sH, sW = shape
+            _lib.check(self._lib.vr_temporal_set_prev(self._h, C.c_void_p(int(up_prev)), sH, sW, sW * 3, 1), self._h)
+        else:
+            a = np.ascontiguousarray(up_prev, dtype=np.uint8)
+            _lib.check(self._lib.vr_temporal_set_prev(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1],
+                                                      a.strides[0], 0), self._h)
+
+    def temporal_get_prev(self, sH: int, sW: int, device_ptr: int | None = None):
+        if device_ptr is not None:
+            _lib.check(self._lib.vr_temporal_get_prev(self._h, C.c_void_p(int(device_ptr)), sH, sW, sW * 3, 1), self._h)
+            return None
+        a = np.empty((sH, sW, 3), np.uint8)
+        _lib.check(self._lib.vr_temporal_get_prev(self._h, a.ctypes.data_as(C.c_void_p), sH, sW, a.strides[0], 0),
+                   self._h)
+        return a
+
+    # -- introspection ---------------------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vr_launch_count(self._h))
+
+    def last_timing(self):
+        t, c = C.c_float(0), C.c_float(0)
+        _lib.check(self._lib.vr_last_timing(self._h, C.byref(t), C.byref(c)), self._h)
+        return float(t.value), float(c.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.vr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+class RealESRGANer:
+    """Signature-compatible stand-in for realesrgan.RealESRGANer as the reference constructs it
+    (video_upscaler.py:328-338). `model` is a model-zoo name or spec instead of an nn.Module; `model_path` may be a
+    .pth (params_ema / params) or None together with `state_dict`."""
+
+    def __init__(self, scale, model_path=None, dni_weight=None, model="RealESRGAN_x4plus", tile=0, tile_pad=10,
+                 pre_pad=10, half=True, device=None, gpu_id=None, state_dict=None, blend="crop"):
+        spec = _as_spec(model)
+        if scale != spec["scale"]:
+            raise ValueError(f"scale={scale} does not match the model's network scale {spec['scale']}")
+        if tile <= 0:
+            # upstream runs the whole frame as one tile when tile == 0; same arithmetic as one tile covering it
+            tile = 1 << 20
+        if not half:
+            raise VrError("the B200 path computes in fp16 with fp32 accumulation; half=False has no CUDA-free fallback")
+        if gpu_id is None:
+            gpu_id = 0
+            if device is not None:
+                idx = getattr(device, "index", None)
+                if idx is None and isinstance(device, str) and ":" in device:
+                    idx = int(device.split(":")[1])
+                gpu_id = idx or 0
+        if state_dict is None:
+            if model_path is None:
+                raise ValueError("either model_path or state_dict is required")
+            import torch
+            loadnet = torch.load(model_path, map_location="cpu")
+            state_dict = loadnet["params_ema"] if "params_ema" in loadnet else loadnet.get("params", loadnet)
+        self.scale = scale
+        self.tile_size = tile
+        self.tile_pad = tile_pad
+        self.pre_pad = pre_pad
+        self.half = half
+        self._r = FrameRestorer(model=spec, state_dict=state_dict, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad,
+                                blend=blend, gpu_id=gpu_id)
+
+    def enhance(self, img, outscale=None, alpha_upsampler="realesrgan"):
+        if outscale is not None and float(outscale) != float(self.scale):
+            raise NotImplementedError("outscale != scale (Lanczos resize) is out of scope; the reference always "
+                                      "passes outscale == scale (video_upscaler.py:501,718)")
+        return self._r.process_frame(img), "RGB"
+
+
+# -- stand-alone filters (host arrays) ------------------------------------------------------------
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("expected uint8 HxWx3")
+    return a
+
+
+def bilateral_filter(img, d=5, sigma_color=25.0, sigma_space=25.0, device=0):
+    a = _u8(img); out = np.empty_like(a)
+    _lib.check(_lib.load().vr_bilateral(device, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1],
+                                        out.ctypes.data_as(C.c_void_p), d, sigma_color, sigma_space))
+    return out
+
+
+def unsharp_mask(img, amount, device=0):
+    a = _u8(img); out = np.empty_like(a)
+    _lib.check(_lib.load().vr_unsharp(device, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1],
+                                      out.ctypes.data_as(C.c_void_p), amount))
+    return out
+
+
+def clahe_bgr(img, clip=2.0, grid=8, device=0, return_tables=False):
+    a = _u8(img); out = np.empty_like(a)
+    hist = np.zeros((grid * grid, 256), np.int32)
+    lut = np.zeros((grid * grid, 256), np.uint8)
+    _lib.check(_lib.load().vr_clahe(device, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1],
+                                    out.ctypes.data_as(C.c_void_p), clip, grid, hist.ctypes.data_as(C.c_void_p),
+                                    lut.ctypes.data_as(C.c_void_p)))
+    return (out, hist, lut) if return_tables else out
+
+
+def temporal_blend(cur, prev, alpha=0.2, tau=12.0, device=0):
+    a = _u8(cur); p = _u8(prev); out = np.empty_like(a)
+    _lib.check(_lib.load().vr_temporal(device, a.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), a.shape[0],
+                                       a.shape[1], out.ctypes.data_as(C.c_void_p), alpha, tau))
+    return out
+
+
+def blend_weights(extent, device=0):
+    w = np.zeros(extent, np.float32)
+    _lib.check(_lib.load().vr_blend_weights(device, extent, w.ctypes.data_as(C.c_void_p)))
+    return w
+
+
+def tile_grid(H, W, tile, tile_pad, scale):
+    lib = _lib.load()
+    n = lib.vr_tile_grid(H, W, tile, tile_pad, scale, None, 0)
+    if n < 0:
+        raise VrError(f"vr_tile_grid: invalid arguments ({n})")
+    tab = np.zeros((n, 12), np.int32)
+    lib.vr_tile_grid(H, W, tile, tile_pad, scale, tab.ctypes.data_as(C.c_void_p), n)
+    return tab
