@@ -52,6 +52,13 @@ class OracleRestorer:
     def reset(self):
         self.prev_up = None
 
+    # same temporal-state surface as the product's FrameRestorer (used by the sharder tests)
+    def temporal_reset(self):
+        self.prev_up = None
+
+    def temporal_set_prev(self, up_prev):
+        self.prev_up = np.ascontiguousarray(up_prev, dtype=np.uint8).copy()
+
     def upscale_only(self, frame: np.ndarray, opts: FrameOpts) -> np.ndarray:
         """Everything except the temporal blend: returns up_t."""
         f = frame
