@@ -1,0 +1,116 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol include/vrb200.h
+declares, the ctypes table matches, error behaviour without a GPU, and the CLI preset table."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = (ROOT / "include" / "vrb200.h").read_text()
+
+
+def declared_symbols():
+    return sorted(set(re.findall(r"\b(vr_[a-z0-9_]+)\s*\(", HEADER)))
+
+
+def test_library_exports_every_declared_symbol():
+    from video_restore_b200 import _lib
+
+    lib = _lib.load()  # raises if the .so is missing: there is no fallback
+    names = declared_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vrb200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes signature table and header disagree"
+
+
+def test_header_cites_reference_interfaces():
+    for cite in ("video_upscaler.py:328-338", "video_upscaler.py:490-505", "video_upscaler.py:496",
+                 "video_upscaler.py:501", "video_upscaler.py:326"):
+        assert cite in HEADER
+
+
+def test_struct_layouts_match_header():
+    from video_restore_b200 import _lib
+
+    assert ctypes.sizeof(_lib.VrConfig) == 16 * 4
+    assert ctypes.sizeof(_lib.VrFrameOpts) == 16 * 4
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this is the CPU-box behaviour")
+    from video_restore_b200._lib import VrError
+    from video_restore_b200.restorer import FrameRestorer, bilateral_filter
+    import numpy as np
+
+    with pytest.raises(VrError, match="no CUDA device|no CPU fallback"):
+        FrameRestorer("RealESRGAN_x4_v3", None)
+    with pytest.raises(VrError):
+        bilateral_filter(np.zeros((8, 8, 3), np.uint8))
+
+
+def test_invalid_configs_rejected_before_touching_a_device():
+    from video_restore_b200 import _lib
+
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    for bad in (dict(model_kind=7), dict(scale=3), dict(tile=0), dict(pre_pad=10), dict(num_feat=48)):
+        kw = dict(model_kind=0, scale=4, num_block=23, num_conv=0, num_feat=64, num_grow_ch=32, tile=512, tile_pad=10,
+                  pre_pad=0, blend=0, device=0)
+        kw.update(bad)
+        cfg = _lib.VrConfig(**kw)
+        assert lib.vr_create(ctypes.byref(cfg), ctypes.byref(h)) == -1, bad
+        assert (lib.vr_last_error(None) or b"") != b""
+    assert lib.vr_tile_grid(0, 10, 8, 2, 4, None, 0) == -1
+
+
+def test_product_never_imports_oracle():
+    for py in (ROOT / "video_restore_b200").glob("*.py"):
+        src = py.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, py
+    for cu in (ROOT / "video_restore_b200" / "csrc").glob("*"):
+        if cu.is_file():
+            assert "oracle/" not in cu.read_text(errors="ignore").replace("oracle/filters.py", "").replace(
+                "oracle.realesrganer", "").replace("spec oracle", "").replace("/ oracle", ""), cu
+
+
+# --- CLI presets: the table at reference video_upscaler.py:687-701 -------------------------------------------
+@pytest.mark.parametrize("argv,tile,overlap,pad,crf,preset", [
+    ([], 1024, 16, 10, 15, "slow"),
+    (["--enhanced"], 512, 32, 32, 15, "slow"),
+    (["--quality", "max"], 1536, 32, 10, 12, "veryslow"),
+    (["--quality", "max", "--enhanced"], 512, 64, 64, 12, "veryslow"),
+    (["--quality", "fast"], 1024, 16, 10, 18, "fast"),
+    (["--quality", "fast", "--enhanced", "--tile-size", "256", "--tile-overlap", "8"], 256, 8, 8, 18, "fast"),
+])
+def test_cli_presets(argv, tile, overlap, pad, crf, preset):
+    from video_restore_b200.cli import build_parser, config_from_args
+
+    cfg = config_from_args(build_parser().parse_args(["in.mp4", "out.mp4", *argv]))
+    assert (cfg.tile_size, cfg.tile_overlap, cfg.tile_pad, cfg.crf, cfg.preset) == (tile, overlap, pad, crf, preset)
+    assert cfg.light_denoise == cfg.enhanced_mode and cfg.use_fp16
+
+
+def test_cli_enhancement_flags():
+    from video_restore_b200.cli import build_parser, config_from_args, frame_opts_from_config
+
+    p = build_parser()
+    cfg = config_from_args(p.parse_args(["a", "b", "--enhanced"]))
+    o = frame_opts_from_config(cfg)
+    assert o.denoise and (o.denoise_d, o.denoise_sigma_color, o.denoise_sigma_space) == (5, 25.0, 25.0)
+    assert o.clahe and o.temporal and cfg.seamless and o.sharpen == pytest.approx(0.1)
+    cfg = config_from_args(p.parse_args(["a", "b", "--enhanced", "--no-seamless", "--no-temporal",
+                                         "--no-color-enhance", "--sharpen", "0.3", "--denoise", "0.3"]))
+    o = frame_opts_from_config(cfg)
+    assert not (cfg.seamless or o.temporal or o.clahe) and o.sharpen == pytest.approx(0.3)
+    assert o.denoise_sigma_color == pytest.approx(50.0)
+    cfg = config_from_args(p.parse_args(["a", "b"]))
+    o = frame_opts_from_config(cfg)
+    assert not (o.denoise or o.clahe or o.temporal or cfg.seamless) and o.sharpen == 0.0
+    assert config_from_args(p.parse_args(["a", "b", "--model", "RealESRGAN_x2plus"])).scale == 2
+    with pytest.raises(SystemExit):
+        p.parse_args(["a", "b", "--model", "nope"])

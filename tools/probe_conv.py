@@ -79,9 +79,8 @@ def main():
         keep = ("vr_conv3x3_test", "vr_global_error", "vr_conv3x3_bench")
         _lib.SIGNATURES = {k: v for k, v in _lib.SIGNATURES.items() if k in keep}
     if group == "basic":
-        case("halo-nocoll", 8, 128, 32, 32, flags=1)
         case("halo-coll", 8, 128, 32, 32)
-        case("halo-2chunk", 8, 128, 64, 32, flags=1)
+        case("halo-2chunk", 8, 128, 64, 32)
     elif group == "shapes":
         case("multi-tile", 37, 300, 64, 32)
         case("cin96", 16, 256, 96, 32)
@@ -100,17 +99,20 @@ def main():
         case("cin12", 12, 140, 12, 64)
         case("rgb", 12, 140, 64, 3)
         case("ps4", 12, 140, 64, 48)
+    elif group == "one":
+        cin, cout = int(sys.argv[2]), int(sys.argv[3])
+        fl = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 0
+        ms = _lib.conv3x3_bench(720, 1280, cin, cout, rows=4, flags=fl, iters=3)
+        print(f"[one] {cin}->{cout} flags={fl}: {ms:.4f} ms  {2.0*720*1280*cin*cout*9/ms/1e9:.1f} TFLOP/s", flush=True)
     elif group == "bench":
         H, W = 720, 1280
-        names = {0: "full", 1: "no-collector", 2: "skip-tma", 4: "skip-mma", 8: "skip-epi", 10: "mma-only",
+        names = {0: "full", 2: "skip-tma", 4: "skip-mma", 8: "skip-epi", 10: "mma-only",
                  12: "tma-only", 6: "epi-only"}
         for cin, cout in [(64, 32), (160, 32), (192, 64), (64, 64)]:
             for rows in (4, 8):
                 if rows == 8 and cout != 32:
                     continue
-                for fl in (0, 1, 2, 4, 8, 10, 12, 6):
-                    if fl == 1 and rows == 8:
-                        continue
+                for fl in (0, 2, 4, 8, 10, 12, 6):
                     try:
                         ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, flags=fl, iters=10)
                         tf = 2.0 * H * W * cin * cout * 9 / ms / 1e9

@@ -11,10 +11,13 @@
 //     conv zero padding. The 9 taps are 9 shared-memory descriptors into that one tile (row shift dx, dy).
 //   * weights pre-packed on the host into the exact swizzled smem image per chunk: one bulk copy per stage.
 //   * accumulators: TH x N fp32 columns of TMEM, double buffered so the epilogue of tile i overlaps the MMAs
-//     of tile i+1. One thread issues all MMAs; MMAs that share an A row tile (same input row, dx, k) are
-//     issued back to back with collector::a fill/use/lastuse so A is read from smem once per input row.
-//   * epilogue (4 warps): tcgen05.ld -> +bias -> LeakyReLU/PReLU -> *s1 + res1 -> *s2 + res2 in fp32 ->
-//     one fp16 rounding -> 16 B stores into a channel slice of the destination NHWC buffer (zero-copy concat).
+//     of tile i+1. One elected thread issues all MMAs. The three dy taps of one input row feed three adjacent
+//     output rows, so they are ONE MMA of N = 3*Cout (B rows = weights of dy 2,1,0): A is read once per
+//     (input row, dx, k) and N is 96 / 192 instead of 32 / 64 (the SS MMA is smem-read bound below N = 128).
+//   * epilogue (8 warps, two groups alternating output rows): tcgen05.ld -> +bias -> LeakyReLU/PReLU ->
+//     *s1 + res1 -> *s2 + res2 in fp32 -> one fp16 rounding -> 16 B stores into a channel slice of the
+//     destination NHWC buffer (zero-copy concat). Residual rows are prefetched before the TMEM loads.
+// Warp roles: 0..7 epilogue (warp % 4 = TMEM lane quarter), 8 = TMA producer, 9 = MMA issuer.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -26,14 +29,14 @@ namespace vr {
 enum ConvAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2 };
 enum ConvOut { OUT_NHWC = 0, OUT_RGB4 = 1, OUT_PS4 = 2 };
 // debug ablation flags (ConvArgs::flags): measurement only
-enum ConvFlags { FLAG_NO_COLLECTOR = 1, FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8 };
+enum ConvFlags { FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8 };
 
 struct ConvArgs {
     int W, H;              // conv input == output extent
     int tiles_x, tiles_y;  // ceil(W/128), ceil(H/TH)
     int nchunks;           // Cin_padded / 32
     int cin_off;           // first input channel inside the source buffer
-    const __half* wpack;   // [nchunks][9][N][32] fp16, pre-swizzled smem image
+    const __half* wpack;   // [nchunks][dx][dy=2,1,0][N][32] fp16, pre-swizzled smem image
     const float* bias;     // [cout]
     const float* prelu;    // [cout] or null
     int act;
@@ -55,33 +58,30 @@ struct ConvArgs {
 constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
 constexpr int next_pow2_c(int x) { int p = 32; while (p < x) p *= 2; return p; }
 
+constexpr int kEpiWarps = 8;
+constexpr int kConvThreads = (kEpiWarps + 2) * 32;
+
 template <int N, int TH>
 struct ConvTraits {
     static constexpr int kInRows = TH + 2;
     static constexpr int kPitch = 130;  // 128 output pixels + 1 halo pixel each side
     static constexpr int kCopyBytes = kInRows * kPitch * 64;  // bytes one TMA box delivers
-    static constexpr int kCopyStride = round_up_c(kCopyBytes, 1024);
-    static constexpr int kAStage = kCopyStride;
+    static constexpr int kAStage = round_up_c(kCopyBytes, 1024);
     static constexpr int kBBytes = 9 * N * 64;
     static constexpr int kBStage = round_up_c(kBBytes, 1024);
     static constexpr int kStageBytes = kAStage + kBStage;
-    static constexpr int kTail = 1024;  // barriers, tmem slot, bias, prelu
-    static constexpr int kBudget = 227 * 1024 - 1024 - kTail;
+    static constexpr int kStatic = 1024;  // static __shared__: barriers, tmem slot, bias / activation tables
+    static constexpr int kBudget = 227 * 1024 - 1024 - kStatic;
     static constexpr int kStagesRaw = kBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 4 ? 4 : (kStagesRaw < 1 ? 1 : kStagesRaw);
     static constexpr int kAccCols = TH * N;
     static constexpr int kTmemCols = next_pow2_c(2 * kAccCols);
-    static constexpr int kSmemBytes = kStages * kStageBytes + kTail + 1024;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + slack for the manual 1024 B alignment
     static_assert(kStagesRaw >= 1, "stage does not fit in shared memory");
     static_assert(kTmemCols <= 512, "accumulators do not fit in TMEM");
     static_assert(N % 16 == 0 && N >= 16 && N <= 64, "N must be 16..64 step 16");
+    static_assert(TH % 2 == 0, "rows alternate between the two epilogue groups");
 };
-
-__device__ __forceinline__ float apply_act(float v, int act, float slope, float pr) {
-    if (act == ACT_LRELU) return v > 0.f ? v : v * slope;
-    if (act == ACT_PRELU) return v > 0.f ? v : v * pr;
-    return v;
-}
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     const __half2* h = reinterpret_cast<const __half2*>(&q);
@@ -100,20 +100,41 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return q;
 }
 
-template <int N, int TH, bool COLL>
-__global__ void __launch_bounds__(192, 1)
+// bias + activation over CNT consecutive channels starting at c0; the mode switch is outside the element loop
+template <int CNT>
+__device__ __forceinline__ void bias_act(float* v, const float* s_bias, const float* s_neg, int c0, int mode) {
+    if (mode == 0) {  // identity
+#pragma unroll
+        for (int j = 0; j < CNT; ++j) v[j] += s_bias[c0 + j];
+    } else if (mode == 1) {  // LeakyReLU with 0 <= slope <= 1: max(t, slope * t)
+#pragma unroll
+        for (int j = 0; j < CNT; ++j) {
+            const float t = v[j] + s_bias[c0 + j];
+            v[j] = fmaxf(t, t * s_neg[c0 + j]);
+        }
+    } else {  // general PReLU / LeakyReLU
+#pragma unroll
+        for (int j = 0; j < CNT; ++j) {
+            const float t = v[j] + s_bias[c0 + j];
+            v[j] = fmaxf(t, 0.f) + s_neg[c0 + j] * fminf(t, 0.f);
+        }
+    }
+}
+
+template <int N, int TH>
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     using T = ConvTraits<N, TH>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* tail = smem + T::kStages * T::kStageBytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+    __shared__ uint64_t s_bars[2 * T::kStages + 4];
+    __shared__ uint32_t s_tmem_slot;
+    __shared__ __align__(16) float s_bias[N];
+    __shared__ __align__(16) float s_neg[N];  // multiplier of the negative part: 1 / slope / PReLU weight
+    uint64_t* full = s_bars;
     uint64_t* empty = full + T::kStages;
     uint64_t* tfull = empty + T::kStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* s_bias = reinterpret_cast<float*>(tail + 128);
-    float* s_prelu = reinterpret_cast<float*>(tail + 128 + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -125,26 +146,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull[i], 1);
-            ptx::mbar_init(&tempty[i], 4);
+            ptx::mbar_init(&tempty[i], kEpiWarps);
         }
         ptx::fence_mbar_init();
     }
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         if (lane == 0) ptx::prefetch_tmap(&tmap);
         __syncwarp();
-        ptx::tmem_alloc<T::kTmemCols>(tmem_slot);
+        ptx::tmem_alloc<T::kTmemCols>(&s_tmem_slot);
     }
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         s_bias[i] = (i < a.cout && a.bias) ? a.bias[i] : 0.f;
-        s_prelu[i] = (i < a.cout && a.prelu) ? a.prelu[i] : 0.f;
+        float neg = 1.f;
+        if (a.act == ACT_LRELU) neg = a.slope;
+        if (a.act == ACT_PRELU) neg = (i < a.cout && a.prelu) ? a.prelu[i] : 0.f;
+        s_neg[i] = neg;
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = s_tmem_slot;
     const int num_tiles = a.tiles_x * a.tiles_y;
 
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0;
@@ -167,11 +191,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kEpiWarps + 1) {
         // ===================== MMA issuer =====================
         // The whole warp walks the (uniform) loop so every address stays on the uniform datapath; one elected
         // lane issues the tcgen05 instructions and the commits.
-        constexpr uint32_t idesc = ptx::make_idesc_f16(128, N);
+        // dy-stacked N: for an input row rho the three taps dy contribute to the three output rows r = rho - dy,
+        // whose accumulators are ADJACENT TMEM column blocks. With the weights of (dy = 2, 1, 0) stored as
+        // consecutive B rows, one MMA of N = 3*Cout updates all three rows and reads the A tile once.
         const bool skip_mma = (a.flags & FLAG_SKIP_MMA) != 0;
         int s = 0;
         uint32_t ph = 0;
@@ -190,34 +216,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                     const uint32_t b_lo0 = a_lo0 + (T::kAStage >> 4);
                     if (!skip_mma) {
 #pragma unroll
-                        for (int rho = 0; rho < T::kInRows; ++rho) {
+                        for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
+                            for (int k = 0; k < 2; ++k) {
 #pragma unroll
-                                for (int k = 0; k < 2; ++k) {
+                                for (int rho = 0; rho < T::kInRows; ++rho) {
                                     const uint32_t a_lo = a_lo0 + (((rho * T::kPitch + dx) * 64 + k * 32) >> 4);
                                     constexpr int kLast = TH - 1;
                                     const int dy_lo = rho - kLast > 0 ? rho - kLast : 0;
                                     const int dy_hi = rho < 2 ? rho : 2;
-#pragma unroll
-                                    for (int dy = 0; dy < 3; ++dy) {
-                                        if (dy < dy_lo || dy > dy_hi) continue;
-                                        const int r = rho - dy;
-                                        const uint32_t b_lo = b_lo0 + ((((dy * 3 + dx) * N) * 64 + k * 32) >> 4);
-                                        const uint32_t acc = (c | dy | dx | k) != 0 ? 1u : 0u;
-                                        const uint32_t d = d_base + r * N;
-                                        if (!COLL || dy_lo == dy_hi)
-                                            ptx::umma_f16<ptx::kCollNone>(d, a_lo, ptx::kDescHiSw64, b_lo,
-                                                                          ptx::kDescHiSw64, idesc, acc);
-                                        else if (dy == dy_lo)
-                                            ptx::umma_f16<ptx::kCollFill>(d, a_lo, ptx::kDescHiSw64, b_lo,
-                                                                          ptx::kDescHiSw64, idesc, acc);
-                                        else if (dy == dy_hi)
-                                            ptx::umma_f16<ptx::kCollLastUse>(d, a_lo, ptx::kDescHiSw64, b_lo,
-                                                                             ptx::kDescHiSw64, idesc, acc);
-                                        else
-                                            ptx::umma_f16<ptx::kCollUse>(d, a_lo, ptx::kDescHiSw64, b_lo,
-                                                                         ptx::kDescHiSw64, idesc, acc);
+                                    const int nblk = dy_hi - dy_lo + 1;
+                                    const int r_lo = rho - dy_hi;
+                                    // B rows of this dx: [dy=2 | dy=1 | dy=0] x N
+                                    const uint32_t b_lo = b_lo0 + ((((dx * 3 + (2 - dy_hi)) * N) * 64 + k * 32) >> 4);
+                                    const uint32_t d = d_base + r_lo * N;
+                                    if (dx == 0 && k == 0 && dy_lo == 0 && c == 0) {
+                                        // the dy = 0 block is the first touch of output row rho in this tile:
+                                        // it must overwrite while the other blocks accumulate -> split the MMA
+                                        if (nblk > 1)
+                                            ptx::umma_f16<ptx::kCollNone>(
+                                                d, a_lo, ptx::kDescHiSw64, b_lo, ptx::kDescHiSw64,
+                                                ptx::make_idesc_f16(128, (nblk > 1 ? nblk - 1 : 1) * N), 1u);
+                                        ptx::umma_f16<ptx::kCollNone>(
+                                            d + (nblk - 1) * N, a_lo, ptx::kDescHiSw64,
+                                            b_lo + (((nblk - 1) * N * 64) >> 4), ptx::kDescHiSw64,
+                                            ptx::make_idesc_f16(128, N), 0u);
+                                    } else {
+                                        ptx::umma_f16<ptx::kCollNone>(d, a_lo, ptx::kDescHiSw64, b_lo,
+                                                                      ptx::kDescHiSw64,
+                                                                      ptx::make_idesc_f16(128, nblk * N), 1u);
                                     }
                                 }
                             }
@@ -231,24 +258,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             }
         }
     } else {
-        // ===================== epilogue warps 0..3 =====================
+        // ===================== epilogue warps 0..7 =====================
+        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int rgrp = warp >> 2;    // rows rgrp, rgrp + 2, ...
+        // activation mode for bias_act: 0 identity, 1 max-form LeakyReLU, 2 general
+        const int amode = a.act == ACT_NONE ? 0 : ((a.act == ACT_LRELU && a.slope >= 0.f && a.slope <= 1.f) ? 1 : 2);
+        const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
-            const int x = tx * 128 + warp * 32 + lane;
+            const int x = tx * 128 + quarter * 32 + lane;
             const int y0 = ty * TH;
+            const bool inb = x < a.W;
             ptx::mbar_wait(&tfull[buf], aph);
             ptx::tc_fence_after();
-            const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * T::kAccCols;
+            const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * T::kAccCols;
             const int r_end = (a.flags & FLAG_SKIP_EPI) ? 0 : TH;
 #pragma unroll 1
-            for (int r = 0; r < r_end; ++r) {
+            for (int r = rgrp; r < r_end; r += 2) {
                 const int y = y0 + r;
                 if (y >= a.H) break;  // warp-uniform
                 const size_t p = static_cast<size_t>(y) * a.W + x;
-                const bool inb = x < a.W;
                 if (a.out_mode == OUT_PS4) {
                     if constexpr (N == 48) {
                         float v[48];
@@ -282,50 +314,59 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                     float v[16];
                     ptx::tmem_ld16(t_row0 + r * N, v);
                     if (inb) {
-                        float o[4];
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch)
-                            o[ch] = apply_act(v[ch] + s_bias[ch], a.act, a.slope, s_prelu[ch]);
-                        o[3] = 0.f;
-                        __half2 h01 = __floats2half2_rn(o[0], o[1]);
-                        __half2 h23 = __floats2half2_rn(o[2], o[3]);
+                        bias_act<4>(v, s_bias, s_neg, 0, amode);
+                        __half2 h01 = __floats2half2_rn(v[0], v[1]);
+                        __half2 h23 = __floats2half2_rn(v[2], 0.f);
                         uint2 q;
                         q.x = *reinterpret_cast<uint32_t*>(&h01);
                         q.y = *reinterpret_cast<uint32_t*>(&h23);
                         *reinterpret_cast<uint2*>(a.out + p * 4) = q;
                     }
                 } else {
+                    if constexpr (N % 32 == 0) {
+                        // all residual loads of the row are issued before the TMEM loads: one global-load latency
+                        // per row instead of one per channel group
+                        constexpr int kVec = N / 8;
+                        uint4 q1[kVec], q2[kVec];
+                        if (inb && has1) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff);
 #pragma unroll
-                    for (int g = 0; g < N / 16; ++g) {
-                        if (g * 16 >= a.cout) break;  // uniform
-                        float v[16];
-                        ptx::tmem_ld16(t_row0 + r * N + g * 16, v);
-                        if (inb) {
-                            const int c0 = g * 16;
+                            for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
+                        }
+                        if (inb && has2) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                v[j] = apply_act(v[j] + s_bias[c0 + j], a.act, a.slope, s_prelu[c0 + j]);
-                            if (a.res1) {
-                                const uint4* rp =
-                                    reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff + c0);
-                                float f[16];
-                                unpack8(rp[0], f);
-                                unpack8(rp[1], f + 8);
+                            for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
+                        }
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], a.s1, f[j]);
+                        for (int g = 0; g < N / 32; ++g) {
+                            float v[32];
+                            ptx::tmem_ld32(t_row0 + r * N + g * 32, v);
+                            if (inb) {
+                                const int c0 = g * 32;
+                                bias_act<32>(v, s_bias, s_neg, c0, amode);
+                                if (has1) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        float f[8];
+                                        unpack8(q1[g * 4 + u], f);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
+                                    }
+                                }
+                                if (has2) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        float f[8];
+                                        unpack8(q2[g * 4 + u], f);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
+                                    }
+                                }
+                                uint4* op = reinterpret_cast<uint4*>(a.out + p * a.out_cstride + a.out_coff + c0);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) op[u] = pack8(v + u * 8);
                             }
-                            if (a.res2) {
-                                const uint4* rp =
-                                    reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff + c0);
-                                float f[16];
-                                unpack8(rp[0], f);
-                                unpack8(rp[1], f + 8);
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], a.s2, f[j]);
-                            }
-                            uint4* op = reinterpret_cast<uint4*>(a.out + p * a.out_cstride + a.out_coff + c0);
-                            op[0] = pack8(v);
-                            op[1] = pack8(v + 8);
                         }
                     }
                 }
@@ -338,7 +379,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         __syncwarp();
         ptx::tmem_dealloc<T::kTmemCols>(tmem_base);
     }

@@ -94,7 +94,9 @@ int pack_conv_weights(Device& dev, const float* w, const float* bias, const floa
                     const int ci = c * 32 + ch;
                     if (ci >= cin) continue;
                     const float v = w[(static_cast<size_t>(n) * cin + ci) * 9 + t];
-                    const size_t row = (static_cast<size_t>(c) * 9 + t) * N + n;
+                    // tap order in smem: dx-major, then dy = 2, 1, 0 (so one B descriptor spans the dy taps)
+                    const int dy = t / 3, dx = t % 3;
+                    const size_t row = (static_cast<size_t>(c) * 9 + dx * 3 + (2 - dy)) * N + n;
                     const int unit = (ch >> 3) ^ ((n >> 1) & 3);
                     img[row * 32 + unit * 8 + (ch & 7)] = __float2half_rn(v);
                 }
@@ -126,10 +128,10 @@ void free_conv_weights(ConvWeights* w) {
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
-template <int N, int TH, bool COLL>
+template <int N, int TH>
 static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     using T = ConvTraits<N, TH>;
-    auto kern = conv3x3_tc_kernel<N, TH, COLL>;
+    auto kern = conv3x3_tc_kernel<N, TH>;
     static bool attr_done[64] = {};
     if (!attr_done[dev.ordinal & 63]) {
         VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes), dev.err);
@@ -139,7 +141,7 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     a.tiles_y = (a.H + TH - 1) / TH;
     const int tiles = a.tiles_x * a.tiles_y;
     const int grid = tiles < dev.sm_count ? tiles : dev.sm_count;
-    kern<<<grid, 192, T::kSmemBytes, dev.stream>>>(tm, a);
+    kern<<<grid, kConvThreads, T::kSmemBytes, dev.stream>>>(tm, a);
     VR_CUDA_CHECK(cudaGetLastError(), dev.err);
     dev.launches++;
     return 0;
@@ -191,19 +193,16 @@ int run_conv(Device& dev, const ConvCall& c) {
         set_error(dev.err, "run_conv: pixel-shuffle output needs cout == 48");
         return -1;
     }
-    const int coll = (c.flags & FLAG_NO_COLLECTOR) ? 0 : 1;
-    const int key = w.npad * 100 + rows * 10 + coll;
+    const int key = w.npad * 100 + rows;
     switch (key) {
-        case 16 * 100 + 4 * 10 + 1: return launch_one<16, 4, true>(dev, tm, a);
-        case 32 * 100 + 4 * 10 + 1: return launch_one<32, 4, true>(dev, tm, a);
-        case 32 * 100 + 8 * 10 + 1: return launch_one<32, 8, true>(dev, tm, a);
-        case 48 * 100 + 4 * 10 + 1: return launch_one<48, 4, true>(dev, tm, a);
-        case 64 * 100 + 4 * 10 + 1: return launch_one<64, 4, true>(dev, tm, a);
-        case 32 * 100 + 4 * 10 + 0: return launch_one<32, 4, false>(dev, tm, a);
-        case 64 * 100 + 4 * 10 + 0: return launch_one<64, 4, false>(dev, tm, a);
+        case 16 * 100 + 4: return launch_one<16, 4>(dev, tm, a);
+        case 32 * 100 + 4: return launch_one<32, 4>(dev, tm, a);
+        case 32 * 100 + 8: return launch_one<32, 8>(dev, tm, a);
+        case 48 * 100 + 4: return launch_one<48, 4>(dev, tm, a);
+        case 64 * 100 + 4: return launch_one<64, 4>(dev, tm, a);
         default:
             set_error(dev.err, "run_conv: no kernel instantiation for N=" + std::to_string(w.npad) +
-                                   " rows=" + std::to_string(rows) + " collector=" + std::to_string(coll));
+                                   " rows=" + std::to_string(rows));
             return -1;
     }
 }
