@@ -104,15 +104,23 @@ def main():
         fl = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 0
         ms = _lib.conv3x3_bench(720, 1280, cin, cout, rows=4, flags=fl, iters=3)
         print(f"[one] {cin}->{cout} flags={fl}: {ms:.4f} ms  {2.0*720*1280*cin*cout*9/ms/1e9:.1f} TFLOP/s", flush=True)
+    elif group == "l2":
+        # same layer on a full 720p image (working set >> L2) and on a 128-row band (fits L2): per-pixel cost
+        for cin, cout in [(64, 32), (160, 32), (192, 64), (64, 64)]:
+            for H in (720, 256, 128, 64):
+                ms = _lib.conv3x3_bench(H, 1280, cin, cout, rows=4, flags=0, iters=20)
+                mb = H * 1280 * (cin + cout) * 2 / 1e6
+                print(f"[l2] {cin}->{cout} H={H:4d} ({mb:6.1f} MB in+out): {ms*1e3:8.1f} us  "
+                      f"{ms*1e6/(H*1280):.4f} ns/px  {2.0*H*1280*cin*cout*9/ms/1e9:.0f} TFLOP/s", flush=True)
     elif group == "bench":
         H, W = 720, 1280
-        names = {0: "full", 2: "skip-tma", 4: "skip-mma", 8: "skip-epi", 10: "mma-only",
+        names = {0: "full", 16: "no-weights-ld", 32: "no-act-ld", 2: "skip-tma", 4: "skip-mma", 8: "skip-epi", 10: "mma-only",
                  12: "tma-only", 6: "epi-only"}
         for cin, cout in [(64, 32), (160, 32), (192, 64), (64, 64)]:
             for rows in (4, 8):
                 if rows == 8 and cout != 32:
                     continue
-                for fl in (0, 2, 4, 8, 10, 12, 6):
+                for fl in (0, 16, 32, 2, 4, 8, 10, 12, 6):
                     try:
                         ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, flags=fl, iters=10)
                         tf = 2.0 * H * W * cin * cout * 9 / ms / 1e9

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -127,9 +128,12 @@ struct Act {
     __half* p;
     int c;  // channels per pixel
 };
+struct Rows {  // output row range of one launch (row-band scheduling); default = all rows
+    int y0 = 0, y1 = -1;
+};
 int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act,
          const __half* res1 = nullptr, int res1_c = 0, float s1 = 1.f, const __half* res2 = nullptr, int res2_c = 0,
-         float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr, int base_c = 0) {
+         float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr, int base_c = 0, Rows rows = Rows()) {
     const ConvWeights* w = layer(h, name);
     if (!w) return fail(h, VR_E_STATE, "missing layer " + name);
     ConvCall c;
@@ -152,7 +156,25 @@ int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out,
     c.out_mode = out_mode;
     c.base = base;
     c.base_cstride = base_c;
+    c.y_begin = rows.y0;
+    c.y_end = rows.y1;
     return run_conv(h->dev, c);
+}
+
+// Optional row-band scheduling of the dense blocks (VR_BAND_MB = band working set in MB; default 0 = off).
+// Measured on B200 (profiles/r1_band_sweep.txt): bit-identical output, but no L2 benefit -- the conv's cost per row
+// is the same for a 64-row and a 720-row image (it is MMA/pipeline bound, not HBM bound) -- while every extra launch
+// costs ~4-10 us, so banding by separate launches only loses. Kept for experiments.
+int band_rows_for(int nh, int nw) {
+    static const int target_mb = []() {
+        const char* e = std::getenv("VR_BAND_MB");
+        return e ? std::atoi(e) : 0;
+    }();
+    if (target_mb <= 0) return nh;
+    long rows = static_cast<long>(target_mb) * 1000000L / (static_cast<long>(nw) * 512L);
+    rows = rows / 4 * 4;
+    if (rows < 16) rows = 16;
+    return rows >= nh ? nh : static_cast<int>(rows);
 }
 
 // RRDBNet.forward on one (already pixel-unshuffled when scale == 2) tile of nh x nw network pixels.
@@ -173,6 +195,7 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
     Act rdb[3] = {{static_cast<__half*>(h->rdb[0].p), 192},
                   {static_cast<__half*>(h->rdb[1].p), 192},
                   {static_cast<__half*>(h->rdb[2].p), 192}};
+    const int band = band_rows_for(nh, nw);
     // conv_first twice: once into `feat` (trunk residual), once into the first RDB buffer's x slot (K = 32: cheap)
     VR_TRY(conv(h, "conv_first", in32, nh, nw, feat, 0, ACT_NONE));
     VR_TRY(conv(h, "conv_first", in32, nh, nw, rdb[0], 0, ACT_NONE));
@@ -180,12 +203,25 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
         for (int r = 0; r < 3; ++r) {
             const std::string pre = "body." + std::to_string(b) + ".rdb" + std::to_string(r + 1) + ".conv";
             Act X = rdb[r], Y = rdb[(r + 1) % 3];
-            for (int k = 1; k <= 4; ++k) VR_TRY(conv(h, pre + std::to_string(k), X, nh, nw, X, 64 + 32 * (k - 1), ACT_LRELU));
-            if (r < 2) {
-                VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f));  // x5*0.2 + x
-            } else {
-                // (x5*0.2 + x)*0.2 + rrdb_in ; rrdb_in lives in rdb[0][:, 0:64] and is overwritten in place
-                VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f, Y.p, 192, 0.2f));
+            // Row bands: conv_k of a band also produces the (5 - k) halo rows above and below that conv_{k+1..5}
+            // of the SAME band need, so x1..x4 are produced and consumed while still in L2 (halo rows are
+            // recomputed by the neighbouring band with identical values).
+            for (int b0 = 0; b0 < nh; b0 += band) {
+                const int b1 = std::min(b0 + band, nh);
+                for (int k = 1; k <= 4; ++k) {
+                    const Rows rr{std::max(b0 - (5 - k), 0), std::min(b1 + (5 - k), nh)};
+                    VR_TRY(conv(h, pre + std::to_string(k), X, nh, nw, X, 64 + 32 * (k - 1), ACT_LRELU, nullptr, 0, 1.f,
+                                nullptr, 0, 1.f, OUT_NHWC, nullptr, 0, rr));
+                }
+                const Rows r5{b0, b1};
+                if (r < 2) {
+                    VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f, nullptr, 0, 1.f, OUT_NHWC,
+                                nullptr, 0, r5));  // x5*0.2 + x
+                } else {
+                    // (x5*0.2 + x)*0.2 + rrdb_in ; rrdb_in lives in rdb[0][:, 0:64] and is overwritten in place
+                    VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f, Y.p, 192, 0.2f, OUT_NHWC,
+                                nullptr, 0, r5));
+                }
             }
         }
     }

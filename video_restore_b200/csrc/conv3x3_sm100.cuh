@@ -29,12 +29,13 @@ namespace vr {
 enum ConvAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2 };
 enum ConvOut { OUT_NHWC = 0, OUT_RGB4 = 1, OUT_PS4 = 2 };
 // debug ablation flags (ConvArgs::flags): measurement only
-enum ConvFlags { FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8 };
+enum ConvFlags { FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8, FLAG_SKIP_B = 16, FLAG_SKIP_A = 32 };
 
 struct ConvArgs {
     int W, H;              // conv input == output extent
-    int tiles_x, tiles_y;  // ceil(W/128), ceil(H/TH)
-    int nchunks;           // Cin_padded / 32
+    int y_begin, y_end;    // output rows [y_begin, y_end) this launch produces (row-band scheduling)
+    int tiles_x, tiles_y;  // ceil(W/128), ceil((y_end - y_begin)/TH)
+    int nchunks;           // Cin_padded / KC
     int cin_off;           // first input channel inside the source buffer
     const __half* wpack;   // [nchunks][dx][dy=2,1,0][N][32] fp16, pre-swizzled smem image
     const float* bias;     // [cout]
@@ -61,22 +62,30 @@ constexpr int next_pow2_c(int x) { int p = 32; while (p < x) p *= 2; return p; }
 constexpr int kEpiWarps = 8;
 constexpr int kConvThreads = (kEpiWarps + 2) * 32;
 
-template <int N, int TH>
+template <int N, int TH, int KC>
 struct ConvTraits {
+    static_assert(KC == 16 || KC == 32, "channels per pipeline stage: 16 (SWIZZLE_32B) or 32 (SWIZZLE_64B)");
+    static constexpr int kRowBytes = KC * 2;  // one pixel's channel chunk
+    static constexpr int kKSteps = KC / 16;   // MMAs (K = 16) per tap and stage
+    static constexpr uint32_t kDescHi = KC == 32 ? ptx::kDescHiSw64 : ptx::kDescHiSw32;
     static constexpr int kInRows = TH + 2;
     static constexpr int kPitch = 130;  // 128 output pixels + 1 halo pixel each side
-    static constexpr int kCopyBytes = kInRows * kPitch * 64;  // bytes one TMA box delivers
+    static constexpr int kCopyBytes = kInRows * kPitch * kRowBytes;  // bytes one TMA box delivers
     static constexpr int kAStage = round_up_c(kCopyBytes, 1024);
-    static constexpr int kBBytes = 9 * N * 64;
+    static constexpr int kBBytes = 9 * N * kRowBytes;
     static constexpr int kBStage = round_up_c(kBBytes, 1024);
     static constexpr int kStageBytes = kAStage + kBStage;
     static constexpr int kStatic = 1024;  // static __shared__: barriers, tmem slot, bias / activation tables
-    static constexpr int kBudget = 227 * 1024 - 1024 - kStatic;
+    // per-warp epilogue staging (NHWC outputs only): 32 pixels x (N fp16 + 16 B pad) for the coalescing transpose
+    static constexpr int kStgPitch = N * 2 + 16;
+    static constexpr int kStgWarp = (N % 32 == 0) ? 32 * kStgPitch : 0;
+    static constexpr int kStgBytes = kEpiWarps * kStgWarp;
+    static constexpr int kBudget = 227 * 1024 - 1024 - kStatic - kStgBytes;
     static constexpr int kStagesRaw = kBudget / kStageBytes;
-    static constexpr int kStages = kStagesRaw > 4 ? 4 : (kStagesRaw < 1 ? 1 : kStagesRaw);
+    static constexpr int kStages = kStagesRaw > 6 ? 6 : (kStagesRaw < 1 ? 1 : kStagesRaw);
     static constexpr int kAccCols = TH * N;
     static constexpr int kTmemCols = next_pow2_c(2 * kAccCols);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + slack for the manual 1024 B alignment
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024;  // + slack for the manual alignment
     static_assert(kStagesRaw >= 1, "stage does not fit in shared memory");
     static_assert(kTmemCols <= 512, "accumulators do not fit in TMEM");
     static_assert(N % 16 == 0 && N >= 16 && N <= 64, "N must be 16..64 step 16");
@@ -121,10 +130,10 @@ __device__ __forceinline__ void bias_act(float* v, const float* s_bias, const fl
     }
 }
 
-template <int N, int TH>
+template <int N, int TH, int KC>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
-    using T = ConvTraits<N, TH>;
+    using T = ConvTraits<N, TH, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t s_bars[2 * T::kStages + 4];
@@ -175,17 +184,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
-                const int x0 = tx * 128, y0 = ty * TH;
+                const int x0 = tx * 128, y0 = a.y_begin + ty * TH;
                 for (int c = 0; c < a.nchunks; ++c) {
                     ptx::mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * T::kStageBytes;
                     if (a.flags & FLAG_SKIP_TMA) {
                         ptx::mbar_arrive(&full[s]);
                     } else {
-                        ptx::mbar_expect_tx(&full[s], T::kCopyBytes + T::kBBytes);
-                        ptx::tma_load_4d(st, &tmap, &full[s], a.cin_off + c * 32, x0 - 1, y0 - 1, 0);
-                        ptx::bulk_load(st + T::kAStage, a.wpack + static_cast<size_t>(c) * 9 * N * 32, T::kBBytes,
-                                       &full[s]);
+                        const bool ld_a = !(a.flags & FLAG_SKIP_A), ld_b = !(a.flags & FLAG_SKIP_B);
+                        ptx::mbar_expect_tx(&full[s], (ld_a ? T::kCopyBytes : 0) + (ld_b ? T::kBBytes : 0));
+                        if (ld_a) ptx::tma_load_4d(st, &tmap, &full[s], a.cin_off + c * KC, x0 - 1, y0 - 1, 0);
+                        if (ld_b)
+                            ptx::bulk_load(st + T::kAStage, a.wpack + static_cast<size_t>(c) * 9 * N * KC, T::kBBytes,
+                                           &full[s]);
                     }
                     if (++s == T::kStages) { s = 0; ph ^= 1; }
                 }
@@ -218,32 +229,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) {
+                            for (int k = 0; k < T::kKSteps; ++k) {
 #pragma unroll
                                 for (int rho = 0; rho < T::kInRows; ++rho) {
-                                    const uint32_t a_lo = a_lo0 + (((rho * T::kPitch + dx) * 64 + k * 32) >> 4);
+                                    const uint32_t a_lo = a_lo0 + (((rho * T::kPitch + dx) * T::kRowBytes + k * 32) >> 4);
                                     constexpr int kLast = TH - 1;
                                     const int dy_lo = rho - kLast > 0 ? rho - kLast : 0;
                                     const int dy_hi = rho < 2 ? rho : 2;
                                     const int nblk = dy_hi - dy_lo + 1;
                                     const int r_lo = rho - dy_hi;
                                     // B rows of this dx: [dy=2 | dy=1 | dy=0] x N
-                                    const uint32_t b_lo = b_lo0 + ((((dx * 3 + (2 - dy_hi)) * N) * 64 + k * 32) >> 4);
+                                    const uint32_t b_lo = b_lo0 + ((((dx * 3 + (2 - dy_hi)) * N) * T::kRowBytes + k * 32) >> 4);
                                     const uint32_t d = d_base + r_lo * N;
                                     if (dx == 0 && k == 0 && dy_lo == 0 && c == 0) {
                                         // the dy = 0 block is the first touch of output row rho in this tile:
                                         // it must overwrite while the other blocks accumulate -> split the MMA
                                         if (nblk > 1)
                                             ptx::umma_f16<ptx::kCollNone>(
-                                                d, a_lo, ptx::kDescHiSw64, b_lo, ptx::kDescHiSw64,
+                                                d, a_lo, T::kDescHi, b_lo, T::kDescHi,
                                                 ptx::make_idesc_f16(128, (nblk > 1 ? nblk - 1 : 1) * N), 1u);
                                         ptx::umma_f16<ptx::kCollNone>(
-                                            d + (nblk - 1) * N, a_lo, ptx::kDescHiSw64,
-                                            b_lo + (((nblk - 1) * N * 64) >> 4), ptx::kDescHiSw64,
+                                            d + (nblk - 1) * N, a_lo, T::kDescHi,
+                                            b_lo + (((nblk - 1) * N * T::kRowBytes) >> 4), T::kDescHi,
                                             ptx::make_idesc_f16(128, N), 0u);
                                     } else {
-                                        ptx::umma_f16<ptx::kCollNone>(d, a_lo, ptx::kDescHiSw64, b_lo,
-                                                                      ptx::kDescHiSw64,
+                                        ptx::umma_f16<ptx::kCollNone>(d, a_lo, T::kDescHi, b_lo,
+                                                                      T::kDescHi,
                                                                       ptx::make_idesc_f16(128, nblk * N), 1u);
                                     }
                                 }
@@ -264,13 +275,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         // activation mode for bias_act: 0 identity, 1 max-form LeakyReLU, 2 general
         const int amode = a.act == ACT_NONE ? 0 : ((a.act == ACT_LRELU && a.slope >= 0.f && a.slope <= 1.f) ? 1 : 2);
         const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
+        uint8_t* stg = smem + T::kStages * T::kStageBytes + warp * T::kStgWarp;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
             const int x = tx * 128 + quarter * 32 + lane;
-            const int y0 = ty * TH;
+            const int y0 = a.y_begin + ty * TH;
             const bool inb = x < a.W;
             ptx::mbar_wait(&tfull[buf], aph);
             ptx::tc_fence_after();
@@ -279,7 +291,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
 #pragma unroll 1
             for (int r = rgrp; r < r_end; r += 2) {
                 const int y = y0 + r;
-                if (y >= a.H) break;  // warp-uniform
+                if (y >= a.y_end) break;  // warp-uniform
                 const size_t p = static_cast<size_t>(y) * a.W + x;
                 if (a.out_mode == OUT_PS4) {
                     if constexpr (N == 48) {
@@ -363,11 +375,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                                         for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
                                     }
                                 }
-                                uint4* op = reinterpret_cast<uint4*>(a.out + p * a.out_cstride + a.out_coff + c0);
+                            }
+                            // stage this pixel's 32 channels (64 B) in the per-warp transpose buffer
+                            uint4* sp = reinterpret_cast<uint4*>(stg + lane * T::kStgPitch + g * 64);
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) op[u] = pack8(v + u * 8);
+                            for (int u = 0; u < 4; ++u) sp[u] = pack8(v + u * 8);
+                        }
+                        __syncwarp();
+                        // coalesced write-out: consecutive lanes write consecutive 16 B units of the same pixel
+                        constexpr int kUnits = N / 8;  // 16 B units per pixel
+                        const int x_base = tx * 128 + quarter * 32;
+                        __half* orow = a.out + (static_cast<size_t>(y) * a.W + x_base) * a.out_cstride + a.out_coff;
+#pragma unroll
+                        for (int i = 0; i < kUnits; ++i) {
+                            const int idx = i * 32 + lane;
+                            const int px = idx / kUnits, un = idx % kUnits;
+                            if (x_base + px < a.W) {
+                                const uint4 val = *reinterpret_cast<const uint4*>(stg + px * T::kStgPitch + un * 16);
+                                *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.out_cstride + un * 8) = val;
                             }
                         }
+                        __syncwarp();
                     }
                 }
             }

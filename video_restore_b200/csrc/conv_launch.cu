@@ -3,6 +3,7 @@
 #include "conv3x3_sm100.cuh"
 #include "vr_common.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -39,8 +40,9 @@ static EncodeTiledFn get_encode_fn(std::string* err) {
 }
 
 // NHWC fp16 activation tensor as a 4-D map (C, W, H, 1); box = 32 channels x pitch pixels x (rows + 2) lines.
-static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int H, int rows, CUtensorMap* out) {
-    auto key = std::make_tuple(static_cast<const void*>(ptr), cstride, W, H, rows);
+static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int H, int rows, int kc,
+                         CUtensorMap* out) {
+    auto key = std::make_tuple(static_cast<const void*>(ptr), cstride, W, H, rows, kc);
     auto it = dev.tmaps.find(key);
     if (it != dev.tmaps.end()) {
         *out = it->second;
@@ -51,11 +53,12 @@ static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 1};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(W) * cstride * 2,
                              static_cast<cuuint64_t>(H) * W * cstride * 2};
-    cuuint32_t box[4] = {32, 130, static_cast<cuuint32_t>(rows + 2), 1};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 130, static_cast<cuuint32_t>(rows + 2), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error(dev.err, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) +
@@ -74,31 +77,44 @@ static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int
 // lands at unit j ^ ((n >> 1) & 3)), i.e. byte-for-byte what the MMA's B descriptor expects in smem.
 // ------------------------------------------------------------------------------------------------
 int pack_conv_weights(Device& dev, const float* w, const float* bias, const float* prelu, int cin, int cout,
-                      ConvWeights* out) {
+                      ConvWeights* out, int kc) {
     if (cin <= 0 || cout <= 0 || cout > 64) {
         set_error(dev.err, "pack_conv_weights: unsupported channel counts");
+        return -1;
+    }
+    if (kc == 0) {
+        static const int env_kc = []() {
+            const char* e = std::getenv("VR_KC");
+            return e ? std::atoi(e) : 32;
+        }();
+        kc = env_kc;
+    }
+    if (kc != 16 && kc != 32) {
+        set_error(dev.err, "pack_conv_weights: kc must be 16 or 32");
         return -1;
     }
     ConvWeights cw;
     cw.cin = cin;
     cw.cout = cout;
+    cw.kc = kc;
     cw.npad = (cout + 15) / 16 * 16;
-    cw.nchunks = (cin + 31) / 32;
+    cw.nchunks = (cin + kc - 1) / kc;
     const int N = cw.npad;
-    const size_t elems = static_cast<size_t>(cw.nchunks) * 9 * N * 32;
+    const size_t elems = static_cast<size_t>(cw.nchunks) * 9 * N * kc;
     std::vector<__half> img(elems, __float2half(0.f));
     for (int c = 0; c < cw.nchunks; ++c)
         for (int t = 0; t < 9; ++t)
             for (int n = 0; n < cout; ++n)
-                for (int ch = 0; ch < 32; ++ch) {
-                    const int ci = c * 32 + ch;
+                for (int ch = 0; ch < kc; ++ch) {
+                    const int ci = c * kc + ch;
                     if (ci >= cin) continue;
                     const float v = w[(static_cast<size_t>(n) * cin + ci) * 9 + t];
                     // tap order in smem: dx-major, then dy = 2, 1, 0 (so one B descriptor spans the dy taps)
                     const int dy = t / 3, dx = t % 3;
                     const size_t row = (static_cast<size_t>(c) * 9 + dx * 3 + (2 - dy)) * N + n;
-                    const int unit = (ch >> 3) ^ ((n >> 1) & 3);
-                    img[row * 32 + unit * 8 + (ch & 7)] = __float2half_rn(v);
+                    // swizzle of K-major rows: 64 B rows: unit ^= (row >> 1) & 3 ; 32 B rows: unit ^= (row >> 2) & 1
+                    const int unit = kc == 32 ? ((ch >> 3) ^ ((n >> 1) & 3)) : ((ch >> 3) ^ ((n >> 2) & 1));
+                    img[row * kc + unit * 8 + (ch & 7)] = __float2half_rn(v);
                 }
     VR_CUDA_CHECK(cudaMalloc(&cw.wpack, elems * sizeof(__half)), dev.err);
     VR_CUDA_CHECK(cudaMemcpyAsync(cw.wpack, img.data(), elems * sizeof(__half), cudaMemcpyHostToDevice, dev.stream),
@@ -128,17 +144,17 @@ void free_conv_weights(ConvWeights* w) {
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
-template <int N, int TH>
+template <int N, int TH, int KC>
 static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
-    using T = ConvTraits<N, TH>;
-    auto kern = conv3x3_tc_kernel<N, TH>;
+    using T = ConvTraits<N, TH, KC>;
+    auto kern = conv3x3_tc_kernel<N, TH, KC>;
     static bool attr_done[64] = {};
     if (!attr_done[dev.ordinal & 63]) {
         VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes), dev.err);
         attr_done[dev.ordinal & 63] = true;
     }
     a.tiles_x = (a.W + 127) / 128;
-    a.tiles_y = (a.H + TH - 1) / TH;
+    a.tiles_y = (a.y_end - a.y_begin + TH - 1) / TH;
     const int tiles = a.tiles_x * a.tiles_y;
     const int grid = tiles < dev.sm_count ? tiles : dev.sm_count;
     kern<<<grid, kConvThreads, T::kSmemBytes, dev.stream>>>(tm, a);
@@ -149,19 +165,22 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
 
 int run_conv(Device& dev, const ConvCall& c) {
     const ConvWeights& w = *c.w;
-    if (c.in_cstride % 8 != 0 || c.cin_off % 8 != 0 || c.cin_off + w.nchunks * 32 > c.in_cstride) {
+    if (c.in_cstride % 8 != 0 || c.cin_off % 8 != 0 || c.cin_off + w.nchunks * w.kc > c.in_cstride) {
         set_error(dev.err, "run_conv: input channel slice not addressable (cstride/offset/chunks)");
         return -1;
     }
     int rows = c.rows;
     if (rows == 0) rows = 4;
     CUtensorMap tm;
-    int rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, rows, &tm);
+    int rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, rows, w.kc, &tm);
     if (rc) return rc;
     ConvArgs a;
     std::memset(&a, 0, sizeof(a));
     a.W = c.W;
     a.H = c.H;
+    a.y_begin = c.y_begin < 0 ? 0 : c.y_begin;
+    a.y_end = (c.y_end < 0 || c.y_end > c.H) ? c.H : c.y_end;
+    if (a.y_end <= a.y_begin) return 0;
     a.nchunks = w.nchunks;
     a.cin_off = c.cin_off;
     a.wpack = w.wpack;
@@ -193,16 +212,21 @@ int run_conv(Device& dev, const ConvCall& c) {
         set_error(dev.err, "run_conv: pixel-shuffle output needs cout == 48");
         return -1;
     }
-    const int key = w.npad * 100 + rows;
+    const int key = (w.npad * 100 + rows) * 100 + w.kc;
     switch (key) {
-        case 16 * 100 + 4: return launch_one<16, 4>(dev, tm, a);
-        case 32 * 100 + 4: return launch_one<32, 4>(dev, tm, a);
-        case 32 * 100 + 8: return launch_one<32, 8>(dev, tm, a);
-        case 48 * 100 + 4: return launch_one<48, 4>(dev, tm, a);
-        case 64 * 100 + 4: return launch_one<64, 4>(dev, tm, a);
+        case (16 * 100 + 4) * 100 + 32: return launch_one<16, 4, 32>(dev, tm, a);
+        case (32 * 100 + 4) * 100 + 32: return launch_one<32, 4, 32>(dev, tm, a);
+        case (32 * 100 + 8) * 100 + 32: return launch_one<32, 8, 32>(dev, tm, a);
+        case (48 * 100 + 4) * 100 + 32: return launch_one<48, 4, 32>(dev, tm, a);
+        case (64 * 100 + 4) * 100 + 32: return launch_one<64, 4, 32>(dev, tm, a);
+        case (16 * 100 + 4) * 100 + 16: return launch_one<16, 4, 16>(dev, tm, a);
+        case (32 * 100 + 4) * 100 + 16: return launch_one<32, 4, 16>(dev, tm, a);
+        case (32 * 100 + 8) * 100 + 16: return launch_one<32, 8, 16>(dev, tm, a);
+        case (48 * 100 + 4) * 100 + 16: return launch_one<48, 4, 16>(dev, tm, a);
+        case (64 * 100 + 4) * 100 + 16: return launch_one<64, 4, 16>(dev, tm, a);
         default:
             set_error(dev.err, "run_conv: no kernel instantiation for N=" + std::to_string(w.npad) +
-                                   " rows=" + std::to_string(rows));
+                                   " rows=" + std::to_string(rows) + " kc=" + std::to_string(w.kc));
             return -1;
     }
 }

@@ -121,6 +121,8 @@ enum CollectorA { kCollNone = 0, kCollFill = 1, kCollUse = 2, kCollLastUse = 3 }
 
 // hi word of a K-major SWIZZLE_64B descriptor with SBO = 512 B (8 rows x 64 B): constant for the whole kernel.
 constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+// same for 32 B rows: SWIZZLE_32B, SBO = 256 B
+constexpr uint32_t kDescHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

@@ -61,7 +61,7 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     if (!sd.ok) return VR_E_NODEVICE;
     Device& dev = sd.dev;
     const size_t px = static_cast<size_t>(t->H) * t->W;
-    const int cin_pad = (t->cin + 31) / 32 * 32;
+    const int cin_pad = (t->cin + 31) / 32 * 32;  // multiple of 32 covers both chunk widths
     const int cout = t->cout;
     const bool rgb4 = (cout == 3);
     const bool ps4 = (cout == 48);

@@ -28,8 +28,9 @@ std::string& global_error();
 struct ConvWeights {
     int cin = 0, cout = 0;
     int npad = 0;     // GEMM N: cout rounded up to 16
-    int nchunks = 0;  // ceil(cin / 32)
-    __half* wpack = nullptr;  // device, [nchunks][9][npad][32] swizzled
+    int kc = 32;      // channels per pipeline stage (16 or 32)
+    int nchunks = 0;  // ceil(cin / kc)
+    __half* wpack = nullptr;  // device, [nchunks][dx][dy=2,1,0][npad][kc] swizzled
     float* bias = nullptr;    // device [cout]
     float* prelu = nullptr;   // device [cout] or null
 };
@@ -39,6 +40,7 @@ struct ConvCall {
     int in_cstride = 0;          // channels per pixel of the source buffer
     int cin_off = 0;
     int H = 0, W = 0;
+    int y_begin = 0, y_end = -1;  // output row range (default: all rows)
     const ConvWeights* w = nullptr;
     int act = 0;
     float slope = 0.2f;
@@ -63,12 +65,12 @@ struct Device {
     cudaStream_t stream = nullptr;
     std::string* err = nullptr;
     int64_t launches = 0;
-    // tensor-map cache: (ptr, cstride, W, H, rows)
-    std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;
+    // tensor-map cache: (ptr, cstride, W, H, rows, kc)
+    std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
 };
 
 int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const float* prelu, int cin, int cout,
-                      ConvWeights* out);
+                      ConvWeights* out, int kc = 0);  // kc = 0: default (env VR_KC or 32)
 void free_conv_weights(ConvWeights* w);
 int run_conv(Device& dev, const ConvCall& c);
 
