@@ -79,7 +79,7 @@ def test_tile_grid_bit_exact(gpu_lib):
         assert np.array_equal(tile_grid(*c), g[f"grid_{i}"]) and np.array_equal(tile_grid(*c), o_tile_grid(*c))
 
 
-@pytest.mark.parametrize("shape", [(97, 131), (64, 64), (5, 7), (240, 427)])
+@pytest.mark.parametrize("shape", [(97, 131), (64, 64), (5, 7), (240, 427), (96, 128), (80, 256), (128, 384)])
 def test_filters_bit_exact_vs_oracle(gpu_lib, shape):
     from oracle import filters as OF
     from video_restore_b200 import restorer as R

@@ -76,6 +76,7 @@ SIGNATURES = {
     "vr_conv3x3_test": (C.c_int, [C.POINTER(VrConvTest)]),
     "vr_global_error": (C.c_char_p, []),
     "vr_conv3x3_bench": (C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_float)]),
+    "vr_filter_bench": (C.c_int, [C.c_int32] * 5 + [C.POINTER(C.c_float)]),
     "vr_launch_count": (C.c_int64, [C.c_void_p]),
     "vr_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
@@ -137,3 +138,17 @@ def conv3x3_bench(H, W, cin, cout, rows=0, flags=0, iters=20, device=0) -> float
     ms = C.c_float(0)
     check(lib.vr_conv3x3_bench(device, H, W, cin, cout, rows, flags, iters, C.byref(ms)))
     return float(ms.value)
+
+
+FILTER_KINDS = {"bilateral": 0, "unsharp": 1, "clahe": 2, "temporal": 3, "post_crop": 4, "post_blend": 5, "pre": 6,
+                "upsample2x": 7}
+# algorithmic bytes per pixel of the HxW frame each kind is timed on
+FILTER_BYTES_PER_PX = {"bilateral": 6, "unsharp": 6, "clahe": 9, "temporal": 9, "post_crop": 11, "post_blend": 11,
+                       "pre": 67, "upsample2x": 128 + 512}
+
+
+def filter_bench(kind: str, H: int, W: int, iters: int = 20, device: int = 0):
+    """Returns (ms per call, achieved GB/s on the algorithmic bytes)."""
+    ms = C.c_float(0)
+    check(load().vr_filter_bench(device, FILTER_KINDS[kind], H, W, iters, C.byref(ms)))
+    return float(ms.value), FILTER_BYTES_PER_PX[kind] * H * W / (ms.value * 1e-3) / 1e9

@@ -75,7 +75,8 @@ struct vr_handle {
     DevBuf lr_in, lr_dn, hr[2], prev_up, stage_in, stage_out;
     bool has_prev = false;
     int prev_h = 0, prev_w = 0;
-    DevBuf clahe_hist, clahe_lut, tile_table;
+    DevBuf clahe_hist, clahe_lut;
+    BlendState blend;
     cudaEvent_t ev_total[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_net;
     size_t ev_used = 0;
@@ -342,9 +343,8 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
         }
     }
     if (blend) {
-        VR_TRY(ensure(h, h->tile_table, grid.size() * 32));
         VR_TRY(launch_post_blend(dev, btiles, tiles_x, tiles_y, cfg.tile * s, cfg.tile_pad * s, up_dst, up_stride, sH,
-                                 sW, h->tile_table.p));
+                                 sW, h->blend));
     }
 
     // (3) enhancement stage on the HR u8 frame; the last stage writes straight into d_out
@@ -474,10 +474,10 @@ void vr_destroy(vr_handle* h) {
     for (auto& kv : h->layers) free_conv_weights(&kv.second);
     DevBuf* bufs[] = {&h->in32, &h->feat, &h->trunk, &h->rdb[0], &h->rdb[1], &h->rdb[2], &h->up1_in, &h->up1_out,
                       &h->up2_in, &h->up2_out, &h->hr_out, &h->sv[0], &h->sv[1], &h->lr_in, &h->lr_dn, &h->hr[0],
-                      &h->hr[1], &h->prev_up, &h->stage_in, &h->stage_out, &h->clahe_hist, &h->clahe_lut,
-                      &h->tile_table};
+                      &h->hr[1], &h->prev_up, &h->stage_in, &h->stage_out, &h->clahe_hist, &h->clahe_lut};
     for (DevBuf* b : bufs) release(*b);
     for (auto& b : h->tile_out) release(b);
+    free_blend_state(h->blend);
     for (auto e : h->ev_net) cudaEventDestroy(e);
     if (h->ev_total[0]) cudaEventDestroy(h->ev_total[0]);
     if (h->ev_total[1]) cudaEventDestroy(h->ev_total[1]);

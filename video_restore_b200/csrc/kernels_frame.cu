@@ -22,6 +22,17 @@ __host__ __device__ inline int reflect101(int i, int n) {
     return m >= n ? period - m : m;
 }
 
+// vectorised fast paths (kernels_frame_vec.cu); each returns false when the shape/alignment is not eligible
+bool try_temporal_vec(Device& dev, const uint8_t* cur, int64_t cstride, const uint8_t* prev, int64_t pstride, int H,
+                      int W, uint8_t* dst, int64_t dstride, float alpha, float tau, int* rc);
+bool try_unsharp_vec(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
+                     float amount, int* rc);
+bool clahe_vec_ok(const uint8_t* src, int64_t sstride, int H, int W, const uint8_t* dst, int64_t dstride, int grid_n);
+int launch_clahe_hist_vec(Device& dev, const uint8_t* src, int64_t sstride, int tile_w, int tile_h, int tiles_x,
+                          int ntiles, int32_t* d_hist);
+int launch_clahe_apply_vec(Device& dev, const uint8_t* src, uint8_t* dst, int H, int W, const uint8_t* d_lut,
+                           int tiles_x, int tiles_y, float inv_tw, float inv_th);
+
 #define VR_LAUNCH_CHECK(dev)                                   \
     do {                                                       \
         VR_CUDA_CHECK(cudaGetLastError(), (dev).err);          \
@@ -135,6 +146,8 @@ int launch_post_crop(Device& dev, const __half* tile, int tile_w, int crop_x0, i
 // ------------------------------------------------------------------------------------------------
 struct BlendTileDev {
     const __half* data;
+    const float* wx;  // g(u), u in [0, pw): precomputed once per tile layout by blend_weights_kernel
+    const float* wy;  // g(v), v in [0, ph)
     int px0, py0, pw, ph;
 };
 __device__ __forceinline__ float blend_g(int u, int extent) {
@@ -154,49 +167,110 @@ int launch_blend_weights(Device& dev, int extent, float* d_w) {
     VR_LAUNCH_CHECK(dev);
     return 0;
 }
-__global__ void post_blend_kernel(const BlendTileDev* __restrict__ tiles, int tiles_x, int tiles_y, int tile_out,
-                                  int pad_out, uint8_t* __restrict__ frame, int64_t stride, int sH, int sW) {
-    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+// PX output pixels per thread (4 when rows are 4-byte aligned: three 32-bit stores; else 1)
+template <int PX>
+__global__ void __launch_bounds__(256)
+post_blend_kernel(const BlendTileDev* __restrict__ tiles, int tiles_x, int tiles_y, int tile_out, int pad_out,
+                  uint8_t* __restrict__ frame, int64_t stride, int sH, int sW) {
+    const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (X >= sW || Y >= sH) return;
-    int ix0 = (X - pad_out) / tile_out; if (X - pad_out < 0) ix0 = 0;
+    if (X0 >= sW || Y >= sH) return;
     int iy0 = (Y - pad_out) / tile_out; if (Y - pad_out < 0) iy0 = 0;
-    int ix1 = (X + pad_out) / tile_out; if (ix1 > tiles_x - 1) ix1 = tiles_x - 1;
     int iy1 = (Y + pad_out) / tile_out; if (iy1 > tiles_y - 1) iy1 = tiles_y - 1;
-    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, wsum = 0.f;
-    for (int ty = iy0; ty <= iy1; ++ty)
-        for (int tx = ix0; tx <= ix1; ++tx) {
-            const BlendTileDev t = tiles[ty * tiles_x + tx];
-            const int u = X - t.px0, v = Y - t.py0;
-            if (u < 0 || u >= t.pw || v < 0 || v >= t.ph) continue;
-            const float w = __fmul_rn(blend_g(v, t.ph), blend_g(u, t.pw));
-            const uint2 q = __ldg(reinterpret_cast<const uint2*>(t.data + (static_cast<size_t>(v) * t.pw + u) * 4));
-            const __half2 rg = *reinterpret_cast<const __half2*>(&q.x);
-            const __half2 b_ = *reinterpret_cast<const __half2*>(&q.y);
-            acc_r = __fadd_rn(acc_r, __fmul_rn(__low2float(rg), w));
-            acc_g = __fadd_rn(acc_g, __fmul_rn(__high2float(rg), w));
-            acc_b = __fadd_rn(acc_b, __fmul_rn(__low2float(b_), w));
-            wsum = __fadd_rn(wsum, w);
-        }
-    uint8_t* o = frame + Y * stride + static_cast<int64_t>(X) * 3;
-    o[0] = quant_u8(__fdiv_rn(acc_b, wsum));
-    o[1] = quant_u8(__fdiv_rn(acc_g, wsum));
-    o[2] = quant_u8(__fdiv_rn(acc_r, wsum));
+    uint8_t outb[PX * 3];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        const int X = X0 + k;
+        int ix0 = (X - pad_out) / tile_out; if (X - pad_out < 0) ix0 = 0;
+        int ix1 = (X + pad_out) / tile_out; if (ix1 > tiles_x - 1) ix1 = tiles_x - 1;
+        float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, wsum = 0.f;
+        for (int ty = iy0; ty <= iy1; ++ty)
+            for (int tx = ix0; tx <= ix1; ++tx) {
+                const BlendTileDev t = tiles[ty * tiles_x + tx];
+                const int u = X - t.px0, v = Y - t.py0;
+                if (u < 0 || u >= t.pw || v < 0 || v >= t.ph) continue;
+                const float w = __fmul_rn(__ldg(t.wy + v), __ldg(t.wx + u));
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(t.data + (static_cast<size_t>(v) * t.pw + u) * 4));
+                const __half2 rg = *reinterpret_cast<const __half2*>(&q.x);
+                const __half2 b_ = *reinterpret_cast<const __half2*>(&q.y);
+                acc_r = __fadd_rn(acc_r, __fmul_rn(__low2float(rg), w));
+                acc_g = __fadd_rn(acc_g, __fmul_rn(__high2float(rg), w));
+                acc_b = __fadd_rn(acc_b, __fmul_rn(__low2float(b_), w));
+                wsum = __fadd_rn(wsum, w);
+            }
+        outb[3 * k + 0] = quant_u8(__fdiv_rn(acc_b, wsum));
+        outb[3 * k + 1] = quant_u8(__fdiv_rn(acc_g, wsum));
+        outb[3 * k + 2] = quant_u8(__fdiv_rn(acc_r, wsum));
+    }
+    uint8_t* o = frame + Y * stride + static_cast<int64_t>(X0) * 3;
+    if (PX == 4) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            o32[j] = outb[4 * j] | (outb[4 * j + 1] << 8) | (outb[4 * j + 2] << 16) |
+                     (static_cast<uint32_t>(outb[4 * j + 3]) << 24);
+    } else {
+        o[0] = outb[0];
+        o[1] = outb[1];
+        o[2] = outb[2];
+    }
 }
 int launch_post_blend(Device& dev, const std::vector<BlendTile>& tiles, int tiles_x, int tiles_y, int tile_out,
-                      int pad_out, uint8_t* frame, int64_t stride, int sH, int sW, void* d_tile_table) {
-    std::vector<BlendTileDev> host(tiles.size());
-    for (size_t i = 0; i < tiles.size(); ++i) host[i] = {tiles[i].data, tiles[i].px0, tiles[i].py0, tiles[i].pw, tiles[i].ph};
-    VR_CUDA_CHECK(cudaMemcpyAsync(d_tile_table, host.data(), host.size() * sizeof(BlendTileDev),
-                                  cudaMemcpyHostToDevice, dev.stream),
-                  dev.err);
-    VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);  // `host` is stack-lifetime
-    dim3 block(32, 8);
-    dim3 grid((sW + 31) / 32, (sH + 7) / 8);
-    post_blend_kernel<<<grid, block, 0, dev.stream>>>(static_cast<const BlendTileDev*>(d_tile_table), tiles_x, tiles_y,
-                                                      tile_out, pad_out, frame, stride, sH, sW);
+                      int pad_out, uint8_t* frame, int64_t stride, int sH, int sW, BlendState& st) {
+    // device tables (tile descriptors + 1-D weight windows) are rebuilt only when the tile layout changes
+    bool same = st.last.size() == tiles.size();
+    for (size_t i = 0; same && i < tiles.size(); ++i)
+        same = st.last[i].data == tiles[i].data && st.last[i].px0 == tiles[i].px0 && st.last[i].py0 == tiles[i].py0 &&
+               st.last[i].pw == tiles[i].pw && st.last[i].ph == tiles[i].ph;
+    if (!same) {
+        size_t nw = 0;
+        for (const BlendTile& t : tiles) nw += static_cast<size_t>(t.pw) + t.ph;
+        VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);  // previous users of the tables
+        if (st.weights_cap < nw) {
+            if (st.d_weights) cudaFree(st.d_weights);
+            VR_CUDA_CHECK(cudaMalloc(&st.d_weights, nw * sizeof(float)), dev.err);
+            st.weights_cap = nw;
+        }
+        const size_t tb = tiles.size() * sizeof(BlendTileDev);
+        if (st.table_cap < tb) {
+            if (st.d_table) cudaFree(st.d_table);
+            VR_CUDA_CHECK(cudaMalloc(&st.d_table, tb), dev.err);
+            st.table_cap = tb;
+        }
+        st.host_table.resize(tb);
+        BlendTileDev* host = reinterpret_cast<BlendTileDev*>(st.host_table.data());
+        size_t off = 0;
+        for (size_t i = 0; i < tiles.size(); ++i) {
+            float* wx = st.d_weights + off;
+            float* wy = wx + tiles[i].pw;
+            off += static_cast<size_t>(tiles[i].pw) + tiles[i].ph;
+            host[i] = {tiles[i].data, wx, wy, tiles[i].px0, tiles[i].py0, tiles[i].pw, tiles[i].ph};
+            int rc = launch_blend_weights(dev, tiles[i].pw, wx);
+            if (rc == 0) rc = launch_blend_weights(dev, tiles[i].ph, wy);
+            if (rc) return rc;
+        }
+        VR_CUDA_CHECK(cudaMemcpyAsync(st.d_table, st.host_table.data(), tb, cudaMemcpyHostToDevice, dev.stream),
+                      dev.err);  // host_table lives in the handle: no sync needed
+        st.last = tiles;
+    }
+    const BlendTileDev* tab = static_cast<const BlendTileDev*>(st.d_table);
+    const bool vec = sW % 4 == 0 && stride % 4 == 0 && (reinterpret_cast<uintptr_t>(frame) & 3) == 0;
+    if (vec) {
+        dim3 block(64, 4);
+        dim3 grid((sW / 4 + 63) / 64, (sH + 3) / 4);
+        post_blend_kernel<4><<<grid, block, 0, dev.stream>>>(tab, tiles_x, tiles_y, tile_out, pad_out, frame, stride, sH, sW);
+    } else {
+        dim3 block(32, 8);
+        dim3 grid((sW + 31) / 32, (sH + 7) / 8);
+        post_blend_kernel<1><<<grid, block, 0, dev.stream>>>(tab, tiles_x, tiles_y, tile_out, pad_out, frame, stride, sH, sW);
+    }
     VR_LAUNCH_CHECK(dev);
     return 0;
+}
+void free_blend_state(BlendState& st) {
+    if (st.d_weights) cudaFree(st.d_weights);
+    if (st.d_table) cudaFree(st.d_table);
+    st = BlendState();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -335,6 +409,8 @@ unsharp_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int W, u
 }
 int launch_unsharp(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
                    float amount) {
+    int vrc = 0;
+    if (try_unsharp_vec(dev, src, sstride, H, W, dst, dstride, amount, &vrc)) return vrc;
     static bool taps_done[64] = {};
     if (!taps_done[dev.ordinal & 63]) {
         double k[7], sum = 0;
@@ -472,16 +548,23 @@ int launch_clahe(Device& dev, const uint8_t* src, int64_t sstride, int H, int W,
     const float lut_scale = 255.0f / static_cast<float>(area);
     const int ntiles = tiles_x * tiles_y;
     VR_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, ntiles * 256 * sizeof(int32_t), dev.stream), dev.err);
-    int chunks = (area + 256 * 16 - 1) / (256 * 16);
-    const int max_chunks = (dev.sm_count * 8 + ntiles - 1) / ntiles;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    clahe_hist_kernel<<<dim3(chunks, ntiles), 256, 0, dev.stream>>>(src, sstride, H, W, tile_w, tile_h, tiles_x,
-                                                                    d_hist);
-    VR_LAUNCH_CHECK(dev);
+    const bool vec = clahe_vec_ok(src, sstride, H, W, dst, dstride, grid_n);
+    if (vec) {
+        int rc = launch_clahe_hist_vec(dev, src, sstride, tile_w, tile_h, tiles_x, ntiles, d_hist);
+        if (rc) return rc;
+    } else {
+        int chunks = (area + 256 * 16 - 1) / (256 * 16);
+        const int max_chunks = (dev.sm_count * 8 + ntiles - 1) / ntiles;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        clahe_hist_kernel<<<dim3(chunks, ntiles), 256, 0, dev.stream>>>(src, sstride, H, W, tile_w, tile_h, tiles_x,
+                                                                        d_hist);
+        VR_LAUNCH_CHECK(dev);
+    }
     clahe_lut_kernel<<<ntiles, 256, 0, dev.stream>>>(d_hist, d_lut, clip, lut_scale);
     VR_LAUNCH_CHECK(dev);
     const float inv_tw = 1.0f / static_cast<float>(tile_w), inv_th = 1.0f / static_cast<float>(tile_h);
+    if (vec) return launch_clahe_apply_vec(dev, src, dst, H, W, d_lut, tiles_x, tiles_y, inv_tw, inv_th);
     clahe_apply_kernel<<<dim3((W + 255) / 256, H), 256, 0, dev.stream>>>(src, sstride, H, W, dst, dstride, d_lut,
                                                                          tiles_x, tiles_y, inv_tw, inv_th);
     VR_LAUNCH_CHECK(dev);
@@ -517,6 +600,8 @@ __global__ void temporal_kernel(const uint8_t* __restrict__ cur, int64_t cstride
 }
 int launch_temporal(Device& dev, const uint8_t* cur, int64_t cstride, const uint8_t* prev, int64_t pstride, int H,
                     int W, uint8_t* dst, int64_t dstride, float alpha, float tau) {
+    int vrc = 0;
+    if (try_temporal_vec(dev, cur, cstride, prev, pstride, H, W, dst, dstride, alpha, tau, &vrc)) return vrc;
     const float one_minus = 1.0f - alpha;
     temporal_kernel<<<dim3((W + 255) / 256, H), 256, 0, dev.stream>>>(cur, cstride, prev, pstride, H, W, dst, dstride,
                                                                       alpha, one_minus, tau);

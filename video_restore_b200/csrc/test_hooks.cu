@@ -212,3 +212,93 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
     free_conv_weights(&cw);
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident timing of the HBM-bound kernels (K0/K2/K3) on synthetic frames.
+// kind: 0 bilateral, 1 unsharp, 2 clahe (hist+lut+apply), 3 temporal, 4 post_crop, 5 post_blend (2x2 tiles),
+//       6 pre, 7 upsample2x(64 ch)
+// ------------------------------------------------------------------------------------------------
+extern "C" int vr_filter_bench(int32_t device, int32_t kind, int32_t H, int32_t W, int32_t iters, float* ms_out) {
+    ScopedDev sd(device);
+    if (!sd.ok) return VR_E_NODEVICE;
+    Device& dev = sd.dev;
+    const size_t fb = static_cast<size_t>(H) * W * 3;
+    const int64_t st = static_cast<int64_t>(W) * 3;
+    uint8_t *a = nullptr, *b = nullptr, *c = nullptr;
+    VR_CUDA_CHECK(cudaMalloc(&a, fb), dev.err);
+    VR_CUDA_CHECK(cudaMalloc(&b, fb), dev.err);
+    VR_CUDA_CHECK(cudaMalloc(&c, fb), dev.err);
+    {
+        std::vector<uint8_t> h(fb);
+        uint32_t s = 99u;
+        for (size_t i = 0; i < fb; ++i) {
+            s = s * 1664525u + 1013904223u;
+            h[i] = static_cast<uint8_t>((i / 3 % W) / 24 + (s >> 28));  // ramp + noise: non-degenerate for every filter
+        }
+        cudaMemcpy(a, h.data(), fb, cudaMemcpyHostToDevice);
+        for (size_t i = 0; i < fb; ++i) h[i] = static_cast<uint8_t>(h[i] + ((i / 7) % 5));
+        cudaMemcpy(b, h.data(), fb, cudaMemcpyHostToDevice);
+    }
+    int32_t* hist = nullptr;
+    uint8_t* lut = nullptr;
+    __half *t0 = nullptr, *t1 = nullptr;
+    void* table = nullptr;
+    BlendState blend_state;
+    cudaMalloc(&hist, 64 * 256 * 4);
+    cudaMalloc(&lut, 64 * 256);
+    cudaMalloc(&table, 4096);
+    const size_t tile_elems = static_cast<size_t>(H) * W * 4;
+    if (kind >= 4) {
+        VR_CUDA_CHECK(cudaMalloc(&t0, kind == 7 ? static_cast<size_t>(H) * W * 4 * 64 * 2 : tile_elems * 2), dev.err);
+        VR_CUDA_CHECK(cudaMemset(t0, 0x38, tile_elems * 2), dev.err);
+        if (kind == 7 || kind == 6) VR_CUDA_CHECK(cudaMalloc(&t1, static_cast<size_t>(H) * W * 64 * 2), dev.err);
+    }
+    auto run = [&]() -> int {
+        switch (kind) {
+            case 0: return launch_bilateral(dev, a, st, H, W, c, st, 5, 25.f, 25.f);
+            case 1: return launch_unsharp(dev, a, st, H, W, c, st, 0.5f);
+            case 2: return launch_clahe(dev, a, st, H, W, c, st, 2.0f, 8, hist, lut, nullptr);
+            case 3: return launch_temporal(dev, a, st, b, st, H, W, c, st, 0.2f, 12.f);
+            case 4: return launch_post_crop(dev, t0, W, 0, 0, W, H, c, st, 0, 0);
+            case 5: {
+                // four overlapping tiles covering the frame (pad = 64 output px), gather-blended
+                const int tw = W / 2, th = H / 2, pad = 64;
+                std::vector<BlendTile> tiles;
+                for (int ty = 0; ty < 2; ++ty)
+                    for (int tx = 0; tx < 2; ++tx) {
+                        const int x0 = tx ? tw - pad : 0, y0 = ty ? th - pad : 0;
+                        tiles.push_back({t0, x0, y0, tw + pad, th + pad});
+                    }
+                return launch_post_blend(dev, tiles, 2, 2, tw, pad, c, st, H, W, blend_state);
+            }
+            case 6: return launch_pre(dev, a, st, H, W, 0, 0, W, H, 0, t1);
+            case 7: return launch_upsample2x(dev, t1, H, W, 64, reinterpret_cast<__half*>(t0));
+            default: set_error(dev.err, "vr_filter_bench: unknown kind"); return VR_E_INVALID;
+        }
+    };
+    int rc = 0;
+    for (int i = 0; i < 3 && rc == 0; ++i) rc = run();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, dev.stream);
+    for (int i = 0; i < iters && rc == 0; ++i) rc = run();
+    cudaEventRecord(e1, dev.stream);
+    cudaError_t se = cudaStreamSynchronize(dev.stream);
+    if (rc == 0 && se != cudaSuccess) {
+        set_error(dev.err, std::string("filter bench kernel failed: ") + cudaGetErrorString(se));
+        rc = VR_E_CUDA;
+    }
+    if (rc == 0) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out = ms / iters;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (void* p : {static_cast<void*>(a), static_cast<void*>(b), static_cast<void*>(c), static_cast<void*>(hist),
+                    static_cast<void*>(lut), static_cast<void*>(t0), static_cast<void*>(t1), table})
+        if (p) cudaFree(p);
+    free_blend_state(blend_state);
+    return rc;
+}

@@ -88,8 +88,17 @@ struct BlendTile {
     const __half* data;  // RGB4 fp16 [ph][pw]
     int px0, py0, pw, ph;  // padded output rect in the scaled frame
 };
+struct BlendState {  // per-handle cache of the blend kernel's device tables (rebuilt when the tile layout changes)
+    std::vector<BlendTile> last;
+    void* d_table = nullptr;
+    size_t table_cap = 0;
+    float* d_weights = nullptr;
+    size_t weights_cap = 0;
+    std::vector<char> host_table;
+};
 int launch_post_blend(Device& dev, const std::vector<BlendTile>& tiles, int tiles_x, int tiles_y, int tile_out,
-                      int pad_out, uint8_t* frame, int64_t stride, int sH, int sW, void* d_tile_table);
+                      int pad_out, uint8_t* frame, int64_t stride, int sH, int sW, BlendState& st);
+void free_blend_state(BlendState& st);
 int launch_bilateral(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
                      int d, float sigma_color, float sigma_space);
 int launch_unsharp(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
