@@ -61,6 +61,11 @@ std::string g_create_error;
 
 }  // namespace
 
+struct Gaps {  // tile-atlas separators in NETWORK pixels (see ConvArgs); empty for a single tile
+    int ngx = 0, ngy = 0;
+    int gx[7] = {0}, gy[7] = {0};
+};
+
 struct vr_handle {
     vr_config cfg;
     Device dev;
@@ -68,6 +73,9 @@ struct vr_handle {
     std::map<std::string, RawTensor> raw;
     std::map<std::string, ConvWeights> layers;
     bool committed = false;
+    Gaps gaps;        // atlas gap mask of the frame being processed (read by conv())
+    int gap_shift = 0;  // log2 of the current layer's resolution multiple
+    int atlas_w = 0, atlas_h = 0;
     // network activations (NHWC fp16), grown on demand
     DevBuf in32, feat, trunk, rdb[3], up1_in, up1_out, up2_in, up2_out, hr_out, sv[2];
     std::vector<DevBuf> tile_out;
@@ -132,6 +140,7 @@ struct Act {
 struct Rows {  // output row range of one launch (row-band scheduling); default = all rows
     int y0 = 0, y1 = -1;
 };
+
 int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act,
          const __half* res1 = nullptr, int res1_c = 0, float s1 = 1.f, const __half* res2 = nullptr, int res2_c = 0,
          float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr, int base_c = 0, Rows rows = Rows()) {
@@ -159,6 +168,13 @@ int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out,
     c.base_cstride = base_c;
     c.y_begin = rows.y0;
     c.y_end = rows.y1;
+    c.ngx = h->gaps.ngx;
+    c.ngy = h->gaps.ngy;
+    c.gshift = h->gap_shift;
+    for (int i = 0; i < 7; ++i) {
+        c.gx[i] = h->gaps.gx[i];
+        c.gy[i] = h->gaps.gy[i];
+    }
     return run_conv(h->dev, c);
 }
 
@@ -230,12 +246,15 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
     Act u1i{static_cast<__half*>(h->up1_in.p), 64}, u1o{static_cast<__half*>(h->up1_out.p), 64};
     Act u2i{static_cast<__half*>(h->up2_in.p), 64}, u2o{static_cast<__half*>(h->up2_out.p), 64};
     VR_TRY(launch_upsample2x(h->dev, trunk.p, nh, nw, 64, u1i.p));
+    h->gap_shift = 1;  // gap columns / rows are 2 pixels wide at 2x, 4 at 4x (nearest upsampling keeps them zero)
     VR_TRY(conv(h, "conv_up1", u1i, 2 * nh, 2 * nw, u1o, 0, ACT_LRELU));
     VR_TRY(launch_upsample2x(h->dev, u1o.p, 2 * nh, 2 * nw, 64, u2i.p));
+    h->gap_shift = 2;
     VR_TRY(conv(h, "conv_up2", u2i, 4 * nh, 4 * nw, u2o, 0, ACT_LRELU));
     VR_TRY(conv(h, "conv_hr", u2o, 4 * nh, 4 * nw, u2i, 0, ACT_LRELU));  // up2_in is dead: reuse for conv_hr out
     Act to{tile_out, 4};
     VR_TRY(conv(h, "conv_last", u2i, 4 * nh, 4 * nw, to, 0, ACT_NONE, nullptr, 0, 1.f, nullptr, 0, 1.f, OUT_RGB4));
+    h->gap_shift = 0;
     return 0;
 }
 
@@ -313,33 +332,73 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
         up_stride = hr_stride;
     }
     const bool blend = cfg.blend == VR_BLEND_GAUSSIAN;
-    if (h->tile_out.size() < (blend ? grid.size() : 1)) h->tile_out.resize(blend ? grid.size() : 1);
-    std::vector<BlendTile> btiles;
+    // Tile atlas: all padded tiles of the frame are packed into ONE network-input image, grid column by grid column,
+    // separated by 1-pixel zero gap columns / rows. A 3x3 conv cannot see across a zero gap that is re-zeroed after
+    // every layer, and the gap is exactly the zero padding tile_process gives each tile, so the result is bit-identical
+    // to running the tiles one by one -- with one launch per layer for the whole frame instead of one per tile.
+    if (tiles_x > 8 || tiles_y > 8)
+        return fail(h, VR_E_INVALID, "more than 8 tiles per axis: use a larger --tile-size");
+    const int net_div = s == 2 ? 2 : 1;  // x2 models run on the pixel-unshuffled (half resolution) grid
+    int colw[8], rowh[8], ax0[8], ay0[8];
     for (size_t ti = 0; ti < grid.size(); ++ti) {
         const TileRect& t = grid[ti];
         const int pw = t.pad_x1 - t.pad_x0, ph = t.pad_y1 - t.pad_y0;
         if (s == 2 && ((pw | ph) & 1))
             return fail(h, VR_E_INVALID,
                         "x2 model: padded tile extent must be even (pixel_unshuffle); use an even tile size/overlap");
-        const int nh = s == 2 ? ph / 2 : ph, nw = s == 2 ? pw / 2 : pw;
-        VR_TRY(ensure(h, h->in32, static_cast<size_t>(nh) * nw * 32 * 2));
-        DevBuf& tob = h->tile_out[blend ? ti : 0];
-        VR_TRY(ensure(h, tob, static_cast<size_t>(ph) * s * pw * s * 4 * 2));
-        VR_TRY(launch_pre(dev, src, sstride, H, W, t.pad_x0, t.pad_y0, pw, ph, s == 2 ? 1 : 0,
-                          static_cast<__half*>(h->in32.p)));
-        cudaEventRecord(next_event(h), dev.stream);
-        if (cfg.model_kind == VR_MODEL_RRDBNET)
-            VR_TRY(run_rrdbnet(h, nh, nw, static_cast<__half*>(tob.p)));
-        else
-            VR_TRY(run_srvgg(h, nh, nw, static_cast<__half*>(tob.p)));
-        cudaEventRecord(next_event(h), dev.stream);
+        colw[ti % tiles_x] = pw / net_div;
+        rowh[ti / tiles_x] = ph / net_div;
+    }
+    Gaps gaps;
+    int Wa = 0, Ha = 0;
+    for (int j = 0; j < tiles_x; ++j) {
+        ax0[j] = Wa;
+        Wa += colw[j];
+        if (j + 1 < tiles_x) gaps.gx[gaps.ngx++] = Wa++;
+    }
+    for (int i = 0; i < tiles_y; ++i) {
+        ay0[i] = Ha;
+        Ha += rowh[i];
+        if (i + 1 < tiles_y) gaps.gy[gaps.ngy++] = Ha++;
+    }
+    const size_t in_bytes = static_cast<size_t>(Ha) * Wa * 32 * 2;
+    const bool in_realloc = h->in32.bytes < in_bytes || !h->in32.p;
+    VR_TRY(ensure(h, h->in32, in_bytes));
+    if (in_realloc || h->atlas_w != Wa || h->atlas_h != Ha) {
+        // gap pixels of the network input are never written by pre_kernel: zero once per layout
+        VR_CUDA_CHECK(cudaMemsetAsync(h->in32.p, 0, in_bytes, dev.stream), dev.err);
+        h->atlas_w = Wa;
+        h->atlas_h = Ha;
+    }
+    if (h->tile_out.empty()) h->tile_out.resize(1);
+    DevBuf& tob = h->tile_out[0];
+    const int out_pitch = Wa * 4;  // every model's network output is 4x the network-input grid
+    VR_TRY(ensure(h, tob, static_cast<size_t>(Ha) * 4 * out_pitch * 4 * 2));
+    for (size_t ti = 0; ti < grid.size(); ++ti) {
+        const TileRect& t = grid[ti];
+        VR_TRY(launch_pre(dev, src, sstride, H, W, t.pad_x0, t.pad_y0, t.pad_x1 - t.pad_x0, t.pad_y1 - t.pad_y0,
+                          s == 2 ? 1 : 0, static_cast<__half*>(h->in32.p), Wa, ax0[ti % tiles_x], ay0[ti / tiles_x]));
+    }
+    h->gaps = gaps;
+    h->gap_shift = 0;
+    cudaEventRecord(next_event(h), dev.stream);
+    if (cfg.model_kind == VR_MODEL_RRDBNET)
+        VR_TRY(run_rrdbnet(h, Ha, Wa, static_cast<__half*>(tob.p)));
+    else
+        VR_TRY(run_srvgg(h, Ha, Wa, static_cast<__half*>(tob.p)));
+    cudaEventRecord(next_event(h), dev.stream);
+    std::vector<BlendTile> btiles;
+    for (size_t ti = 0; ti < grid.size(); ++ti) {
+        const TileRect& t = grid[ti];
+        const int pw = t.pad_x1 - t.pad_x0, ph = t.pad_y1 - t.pad_y0;
+        const __half* origin = static_cast<const __half*>(tob.p) +
+                               (static_cast<size_t>(ay0[ti / tiles_x]) * 4 * out_pitch + ax0[ti % tiles_x] * 4) * 4;
         if (blend) {
-            btiles.push_back({static_cast<const __half*>(tob.p), t.pad_x0 * s, t.pad_y0 * s, pw * s, ph * s});
+            btiles.push_back({origin, t.pad_x0 * s, t.pad_y0 * s, pw * s, ph * s, out_pitch});
         } else {
             const int dx0 = t.in_x0 * s, dy0 = t.in_y0 * s;
             const int w = std::min(t.in_x1 * s, sW) - dx0, hh = std::min(t.in_y1 * s, sH) - dy0;  // un-pad (post_process)
-            VR_TRY(launch_post_crop(dev, static_cast<const __half*>(tob.p), pw * s, t.out_x0, t.out_y0, w, hh, up_dst,
-                                    up_stride, dx0, dy0));
+            VR_TRY(launch_post_crop(dev, origin, out_pitch, t.out_x0, t.out_y0, w, hh, up_dst, up_stride, dx0, dy0));
         }
     }
     if (blend) {

@@ -54,6 +54,11 @@ struct ConvArgs {
     const __half* base;  // OUT_PS4: network input (RGB in channels 0..2), added to the 16 sub-pixels
     int base_cstride;
     int flags;  // ConvFlags
+    // Tile atlas: several RealESRGANer tiles share one image, separated by zero gap columns / rows (the gap IS the
+    // per-tile zero padding). Outputs at gap positions are forced to zero so the separation survives every layer.
+    // A position x is a gap iff (x >> gshift) == gx[j] for some j (gshift = log2 of the resolution multiple).
+    int ngx, ngy, gshift;
+    int gx[7], gy[7];
 };
 
 constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
@@ -284,6 +289,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             const int x = tx * 128 + quarter * 32 + lane;
             const int y0 = a.y_begin + ty * TH;
             const bool inb = x < a.W;
+            bool xgap = false;
+            for (int j = 0; j < a.ngx; ++j) xgap |= ((x >> a.gshift) == a.gx[j]);
             ptx::mbar_wait(&tfull[buf], aph);
             ptx::tc_fence_after();
             const uint32_t t_row0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * T::kAccCols;
@@ -293,6 +300,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 const int y = y0 + r;
                 if (y >= a.y_end) break;  // warp-uniform
                 const size_t p = static_cast<size_t>(y) * a.W + x;
+                bool gap = xgap;
+                for (int j = 0; j < a.ngy; ++j) gap |= ((y >> a.gshift) == a.gy[j]);
                 if (a.out_mode == OUT_PS4) {
                     if constexpr (N == 48) {
                         float v[48];
@@ -375,6 +384,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                                         for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
                                     }
                                 }
+                            }
+                            if (gap) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = 0.f;
                             }
                             // stage this pixel's 32 channels (64 B) in the per-warp transpose buffer
                             uint4* sp = reinterpret_cast<uint4*>(stg + lane * T::kStgPitch + g * 64);

@@ -204,6 +204,13 @@ int run_conv(Device& dev, const ConvCall& c) {
     a.base = c.base;
     a.base_cstride = c.base_cstride;
     a.flags = c.flags;
+    a.ngx = c.ngx;
+    a.ngy = c.ngy;
+    a.gshift = c.gshift;
+    for (int i = 0; i < 7; ++i) {
+        a.gx[i] = c.gx[i];
+        a.gy[i] = c.gy[i];
+    }
     if (c.out_mode == OUT_NHWC && (w.cout % 16 != 0 || c.out_cstride % 8 != 0 || c.out_coff % 8 != 0)) {
         set_error(dev.err, "run_conv: NHWC output needs cout % 16 == 0 and 16-byte aligned channel slices");
         return -1;

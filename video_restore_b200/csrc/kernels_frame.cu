@@ -69,7 +69,7 @@ int launch_upsample2x(Device& dev, const __half* src, int H, int W, int C, __hal
 // K0 pre: one thread per output pixel, 64 B (32 fp16 channels) stored as 4 x uint4
 // ------------------------------------------------------------------------------------------------
 __global__ void pre_kernel(const uint8_t* __restrict__ frame, int64_t stride, int H, int W, int x0, int y0, int w,
-                           int h, int unshuffle, __half* __restrict__ dst) {
+                           int h, int unshuffle, __half* __restrict__ dst, int dst_pitch, int dst_x0, int dst_y0) {
     const int ow = unshuffle ? w / 2 : w;
     const int oh = unshuffle ? h / 2 : h;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,15 +97,16 @@ __global__ void pre_kernel(const uint8_t* __restrict__ frame, int64_t stride, in
                     v[c * 4 + dy * 2 + dx] = __float2half_rn(__fdiv_rn(static_cast<float>(p[2 - c]), inv255));
             }
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + static_cast<size_t>(idx) * 32);
+    uint4* o = reinterpret_cast<uint4*>(dst + (static_cast<size_t>(dst_y0 + oy) * dst_pitch + dst_x0 + ox) * 32);
     const uint4* s = reinterpret_cast<const uint4*>(v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = s[i];
 }
 int launch_pre(Device& dev, const uint8_t* frame, int64_t stride, int H, int W, int x0, int y0, int w, int h,
-               int unshuffle, __half* dst) {
+               int unshuffle, __half* dst, int dst_pitch, int dst_x0, int dst_y0) {
     const int n = unshuffle ? (w / 2) * (h / 2) : w * h;
-    pre_kernel<<<(n + 255) / 256, 256, 0, dev.stream>>>(frame, stride, H, W, x0, y0, w, h, unshuffle, dst);
+    pre_kernel<<<(n + 255) / 256, 256, 0, dev.stream>>>(frame, stride, H, W, x0, y0, w, h, unshuffle, dst, dst_pitch,
+                                                        dst_x0, dst_y0);
     VR_LAUNCH_CHECK(dev);
     return 0;
 }
@@ -146,6 +147,7 @@ int launch_post_crop(Device& dev, const __half* tile, int tile_w, int crop_x0, i
 // ------------------------------------------------------------------------------------------------
 struct BlendTileDev {
     const __half* data;
+    int pitch;        // pixels per tile row in memory (atlas pitch)
     const float* wx;  // g(u), u in [0, pw): precomputed once per tile layout by blend_weights_kernel
     const float* wy;  // g(v), v in [0, ph)
     int px0, py0, pw, ph;
@@ -190,7 +192,7 @@ post_blend_kernel(const BlendTileDev* __restrict__ tiles, int tiles_x, int tiles
                 const int u = X - t.px0, v = Y - t.py0;
                 if (u < 0 || u >= t.pw || v < 0 || v >= t.ph) continue;
                 const float w = __fmul_rn(__ldg(t.wy + v), __ldg(t.wx + u));
-                const uint2 q = __ldg(reinterpret_cast<const uint2*>(t.data + (static_cast<size_t>(v) * t.pw + u) * 4));
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(t.data + (static_cast<size_t>(v) * t.pitch + u) * 4));
                 const __half2 rg = *reinterpret_cast<const __half2*>(&q.x);
                 const __half2 b_ = *reinterpret_cast<const __half2*>(&q.y);
                 acc_r = __fadd_rn(acc_r, __fmul_rn(__low2float(rg), w));
@@ -221,7 +223,7 @@ int launch_post_blend(Device& dev, const std::vector<BlendTile>& tiles, int tile
     bool same = st.last.size() == tiles.size();
     for (size_t i = 0; same && i < tiles.size(); ++i)
         same = st.last[i].data == tiles[i].data && st.last[i].px0 == tiles[i].px0 && st.last[i].py0 == tiles[i].py0 &&
-               st.last[i].pw == tiles[i].pw && st.last[i].ph == tiles[i].ph;
+               st.last[i].pw == tiles[i].pw && st.last[i].ph == tiles[i].ph && st.last[i].pitch == tiles[i].pitch;
     if (!same) {
         size_t nw = 0;
         for (const BlendTile& t : tiles) nw += static_cast<size_t>(t.pw) + t.ph;
@@ -244,7 +246,7 @@ int launch_post_blend(Device& dev, const std::vector<BlendTile>& tiles, int tile
             float* wx = st.d_weights + off;
             float* wy = wx + tiles[i].pw;
             off += static_cast<size_t>(tiles[i].pw) + tiles[i].ph;
-            host[i] = {tiles[i].data, wx, wy, tiles[i].px0, tiles[i].py0, tiles[i].pw, tiles[i].ph};
+            host[i] = {tiles[i].data, tiles[i].pitch, wx, wy, tiles[i].px0, tiles[i].py0, tiles[i].pw, tiles[i].ph};
             int rc = launch_blend_weights(dev, tiles[i].pw, wx);
             if (rc == 0) rc = launch_blend_weights(dev, tiles[i].ph, wy);
             if (rc) return rc;

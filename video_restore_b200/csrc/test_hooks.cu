@@ -267,11 +267,11 @@ extern "C" int vr_filter_bench(int32_t device, int32_t kind, int32_t H, int32_t 
                 for (int ty = 0; ty < 2; ++ty)
                     for (int tx = 0; tx < 2; ++tx) {
                         const int x0 = tx ? tw - pad : 0, y0 = ty ? th - pad : 0;
-                        tiles.push_back({t0, x0, y0, tw + pad, th + pad});
+                        tiles.push_back({t0, x0, y0, tw + pad, th + pad, tw + pad});
                     }
                 return launch_post_blend(dev, tiles, 2, 2, tw, pad, c, st, H, W, blend_state);
             }
-            case 6: return launch_pre(dev, a, st, H, W, 0, 0, W, H, 0, t1);
+            case 6: return launch_pre(dev, a, st, H, W, 0, 0, W, H, 0, t1, W, 0, 0);
             case 7: return launch_upsample2x(dev, t1, H, W, 64, reinterpret_cast<__half*>(t0));
             default: set_error(dev.err, "vr_filter_bench: unknown kind"); return VR_E_INVALID;
         }

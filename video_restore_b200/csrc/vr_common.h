@@ -56,6 +56,9 @@ struct ConvCall {
     const __half* base = nullptr;
     int base_cstride = 0;
     int rows = 0;   // output rows per CTA tile (TH), 0 = default
+    // tile-atlas gap mask (see ConvArgs): gap columns / rows in units of (1 << gshift) pixels
+    int ngx = 0, ngy = 0, gshift = 0;
+    int gx[7] = {0}, gy[7] = {0};
     int flags = 0;  // ConvFlags (debug ablations)
 };
 
@@ -78,15 +81,17 @@ int run_conv(Device& dev, const ConvCall& c);
 int launch_upsample2x(Device& dev, const __half* src, int H, int W, int C, __half* dst);
 // u8 BGR frame rect -> fp16 RGB NHWC32 (zero padded channels); reflect pads past the frame edge;
 // unshuffle=1 applies pixel_unshuffle(2) (12 channels, c*4 + dy*2 + dx)
+// dst is an NHWC32 image of `dst_pitch` pixels per row; the tile lands at (dst_x0, dst_y0)
 int launch_pre(Device& dev, const uint8_t* frame, int64_t stride, int H, int W, int x0, int y0, int w, int h,
-               int unshuffle, __half* dst);
+               int unshuffle, __half* dst, int dst_pitch, int dst_x0, int dst_y0);
 // RGB4 fp16 tile -> clamp, *255, rint, BGR u8 into the frame rect
 int launch_post_crop(Device& dev, const __half* tile, int tile_w, int crop_x0, int crop_y0, int w, int h,
                      uint8_t* frame, int64_t stride, int dst_x0, int dst_y0);
 
 struct BlendTile {
-    const __half* data;  // RGB4 fp16 [ph][pw]
+    const __half* data;  // RGB4 fp16, first pixel of the tile; rows are `pitch` pixels apart
     int px0, py0, pw, ph;  // padded output rect in the scaled frame
+    int pitch;
 };
 struct BlendState {  // per-handle cache of the blend kernel's device tables (rebuilt when the tile layout changes)
     std::vector<BlendTile> last;
