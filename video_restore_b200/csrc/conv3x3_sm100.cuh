@@ -181,6 +181,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_slot;
     const int num_tiles = a.tiles_x * a.tiles_y;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, bias table; weights and bias are
+    // never written by a kernel) overlaps the previous layer's tail. The next layer may start launching now; this
+    // layer's activations / residuals are only touched after the previous grid has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == kEpiWarps) {
         // ===================== TMA producer =====================

@@ -157,8 +157,17 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     a.tiles_y = (a.y_end - a.y_begin + TH - 1) / TH;
     const int tiles = a.tiles_x * a.tiles_y;
     const int grid = tiles < dev.sm_count ? tiles : dev.sm_count;
-    kern<<<grid, kConvThreads, T::kSmemBytes, dev.stream>>>(tm, a);
-    VR_CUDA_CHECK(cudaGetLastError(), dev.err);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = T::kSmemBytes;
+    cfg.stream = dev.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: prologue overlaps the previous kernel
+    attr[0].val.programmaticStreamSerializationAllowed = dev.use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
     dev.launches++;
     return 0;
 }
