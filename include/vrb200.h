@@ -147,6 +147,9 @@ const char* vr_global_error(void);
 int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t rows,
                      int32_t flags, int32_t iters, float* ms_out);
 
+/* SM cycles (clock64) the slowest CTA spent inside the last vr_conv3x3_bench launch: cycles / time = real SM clock. */
+int64_t vr_last_conv_cycles(void);
+
 /* Device-resident timing of the HBM-bound kernels on a synthetic HxW uint8 frame (average ms per call).
  * kind: 0 bilateral, 1 unsharp, 2 CLAHE (hist+LUT+apply), 3 temporal, 4 post crop-merge, 5 post Gaussian blend (2x2
  * tiles), 6 pre (u8 -> fp16 NHWC32), 7 nearest x2 upsample (64 channels). */

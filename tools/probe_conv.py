@@ -124,8 +124,9 @@ def main():
                     try:
                         ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, flags=fl, iters=10)
                         tf = 2.0 * H * W * cin * cout * 9 / ms / 1e9
-                        print(f"[bench] {cin}->{cout} rows={rows} {names[fl]:>12}: {ms:.4f} ms  {tf:.1f} TFLOP/s",
-                              flush=True)
+                        cyc = _lib.last_conv_cycles()
+                        print(f"[bench] {cin}->{cout} rows={rows} {names[fl]:>12}: {ms:.4f} ms  {tf:.1f} TFLOP/s  "
+                              f"{cyc} cyc/CTA -> {cyc / (ms * 1e3):.0f} MHz", flush=True)
                     except Exception as e:  # noqa: BLE001
                         print(f"[bench] {cin}->{cout} rows={rows} flags={fl}: ERROR {e}", flush=True)
                         return

@@ -76,6 +76,7 @@ SIGNATURES = {
     "vr_conv3x3_test": (C.c_int, [C.POINTER(VrConvTest)]),
     "vr_global_error": (C.c_char_p, []),
     "vr_conv3x3_bench": (C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_float)]),
+    "vr_last_conv_cycles": (C.c_int64, []),
     "vr_filter_bench": (C.c_int, [C.c_int32] * 5 + [C.POINTER(C.c_float)]),
     "vr_launch_count": (C.c_int64, [C.c_void_p]),
     "vr_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -138,6 +139,10 @@ def conv3x3_bench(H, W, cin, cout, rows=0, flags=0, iters=20, device=0) -> float
     ms = C.c_float(0)
     check(lib.vr_conv3x3_bench(device, H, W, cin, cout, rows, flags, iters, C.byref(ms)))
     return float(ms.value)
+
+
+def last_conv_cycles() -> int:
+    return int(load().vr_last_conv_cycles())
 
 
 FILTER_KINDS = {"bilateral": 0, "unsharp": 1, "clahe": 2, "temporal": 3, "post_crop": 4, "post_blend": 5, "pre": 6,

@@ -17,7 +17,7 @@
 //   * epilogue (8 warps, two groups alternating output rows): tcgen05.ld -> +bias -> LeakyReLU/PReLU ->
 //     *s1 + res1 -> *s2 + res2 in fp32 -> one fp16 rounding -> 16 B stores into a channel slice of the
 //     destination NHWC buffer (zero-copy concat). Residual rows are prefetched before the TMEM loads.
-// Warp roles: 0..7 epilogue (warp % 4 = TMEM lane quarter), 8 = TMA producer, 9 = MMA issuer.
+// Warp roles: 0..7 epilogue (warp % 4 = TMEM lane quarter), 8 = TMA producer, 9 and 10 = MMA issuers (alternating stages).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -59,13 +59,15 @@ struct ConvArgs {
     // A position x is a gap iff (x >> gshift) == gx[j] for some j (gshift = log2 of the resolution multiple).
     int ngx, ngy, gshift;
     int gx[7], gy[7];
+    long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 
 constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
 constexpr int next_pow2_c(int x) { int p = 32; while (p < x) p *= 2; return p; }
 
 constexpr int kEpiWarps = 8;
-constexpr int kConvThreads = (kEpiWarps + 2) * 32;
+constexpr int kMmaWarps = 2;  // two issuers ping-pong pipeline stages (see the MMA section)
+constexpr int kConvThreads = (kEpiWarps + 1 + kMmaWarps) * 32;
 
 template <int N, int TH, int KC>
 struct ConvTraits {
@@ -152,6 +154,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const long long t_start = clock64();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < T::kStages; ++i) {
@@ -159,7 +162,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             ptx::mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&tfull[i], 1);
+            ptx::mbar_init(&tfull[i], kMmaWarps);  // every issuer commits its own MMAs of the tile
             ptx::mbar_init(&tempty[i], kEpiWarps);
         }
         ptx::fence_mbar_init();
@@ -212,10 +215,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 }
             }
         }
-    } else if (warp == kEpiWarps + 1) {
-        // ===================== MMA issuer =====================
-        // The whole warp walks the (uniform) loop so every address stays on the uniform datapath; one elected
-        // lane issues the tcgen05 instructions and the commits.
+    } else if (warp > kEpiWarps) {
+        // ===================== MMA issuers (two warps, alternating pipeline stages) =====================
+        // Each warp walks the whole (uniform) loop so every address stays on the uniform datapath; one elected lane
+        // issues the tcgen05 instructions and the commits. Measured (tools/mma_queue_probe, mma_commit_probe): the
+        // tensor pipe queues only ~8 MMAs (~400 cycles of work) and reading an mbarrier completed by TMA or
+        // tcgen05.commit costs the reader ~250 cycles, so a single issuer drains the queue at every stage boundary
+        // (~830 cycles lost per 36-MMA stage). With two issuers, warp w owns the stages with (global stage index) % 2
+        // == w: it does its barrier waits while the other warp is issuing, then takes over through a named barrier, so
+        // issue order stays deterministic (~320 cycles lost per stage; polling the next barrier mid-stage from a single
+        // issuer was tried and is slower).
+        const int mw = warp - (kEpiWarps + 1);  // 0 or 1
+        int gstage = 0;                         // global stage counter over all tiles of this CTA
         // dy-stacked N: for an input row rho the three taps dy contribute to the three output rows r = rho - dy,
         // whose accumulators are ADJACENT TMEM column blocks. With the weights of (dy = 2, 1, 0) stored as
         // consecutive B rows, one MMA of N = 3*Cout updates all three rows and reads the A tile once.
@@ -230,9 +241,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             ptx::tc_fence_after();
             const uint32_t d_base = tmem_base + buf * T::kAccCols;
             for (int c = 0; c < a.nchunks; ++c) {
-                ptx::mbar_wait(&full[s], ph);
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) {
+                const bool mine = (gstage & 1) == mw;
+                if (mine) {
+                    ptx::mbar_wait(&full[s], ph);
+                    ptx::tc_fence_after();
+                    // hand-over: wait until the other warp has issued the previous stage (barrier id 1 + mw).
+                    // BAR.SYNC blocks lazily (at the next dependent instruction), which is all that is needed here.
+                    if (gstage > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+                }
+                if (mine && ptx::elect_one()) {
                     const uint32_t a_lo0 = (ptx::smem_u32(smem + s * T::kStageBytes) >> 4);
                     const uint32_t b_lo0 = a_lo0 + (T::kAStage >> 4);
                     if (!skip_mma) {
@@ -272,12 +289,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                         }
                     }
                     ptx::umma_commit(&empty[s]);
-                    if (c == a.nchunks - 1) ptx::umma_commit(&tfull[buf]);
                 }
                 __syncwarp();
+                if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");  // other warp may issue next
+                ++gstage;
                 if (++s == T::kStages) { s = 0; ph ^= 1; }
             }
+            // this warp's MMAs of the tile are all issued: its commit is one of the kMmaWarps arrivals on tfull
+            if (ptx::elect_one()) ptx::umma_commit(&tfull[buf]);
+            __syncwarp();
         }
+        // consume the last, unmatched bar.arrive so no named barrier is left half-arrived
+        if (gstage > 0 && (gstage & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
     } else {
         // ===================== epilogue warps 0..7 =====================
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32)
@@ -429,6 +452,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         __syncwarp();
         ptx::tmem_dealloc<T::kTmemCols>(tmem_base);
     }
+    if (a.dbg_cycles && threadIdx.x == 0) a.dbg_cycles[blockIdx.x] = clock64() - t_start;
 }
 
 }  // namespace vr

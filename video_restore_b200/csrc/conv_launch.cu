@@ -213,6 +213,7 @@ int run_conv(Device& dev, const ConvCall& c) {
     a.base = c.base;
     a.base_cstride = c.base_cstride;
     a.flags = c.flags;
+    a.dbg_cycles = c.dbg_cycles;
     a.ngx = c.ngx;
     a.ngy = c.ngy;
     a.gshift = c.gshift;

@@ -10,6 +10,8 @@
 using namespace vr;
 
 extern "C" const char* vr_global_error(void) { return global_error().c_str(); }
+static long long g_last_conv_cycles = 0;
+extern "C" int64_t vr_last_conv_cycles(void) { return g_last_conv_cycles; }
 
 namespace {
 struct ScopedDev {
@@ -188,6 +190,10 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
     c.out_mode = (cout == 3) ? OUT_RGB4 : OUT_NHWC;
     c.rows = rows;
     c.flags = flags;
+    long long* d_cyc = nullptr;
+    cudaMalloc(&d_cyc, 512 * sizeof(long long));
+    cudaMemset(d_cyc, 0, 512 * sizeof(long long));
+    c.dbg_cycles = d_cyc;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -204,11 +210,17 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         *ms_out = ms / iters;
+        long long hc[256];
+        cudaMemcpy(hc, d_cyc, sizeof(hc), cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (int i = 0; i < 256; ++i) mx = hc[i] > mx ? hc[i] : mx;
+        g_last_conv_cycles = mx;  // slowest CTA of the last launch
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(dx);
     cudaFree(dy);
+    cudaFree(d_cyc);
     free_conv_weights(&cw);
     return rc;
 }

@@ -60,6 +60,7 @@ struct ConvCall {
     int ngx = 0, ngy = 0, gshift = 0;
     int gx[7] = {0}, gy[7] = {0};
     int flags = 0;  // ConvFlags (debug ablations)
+    long long* dbg_cycles = nullptr;
 };
 
 struct Device {
