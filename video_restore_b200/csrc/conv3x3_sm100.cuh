@@ -59,6 +59,11 @@ struct ConvArgs {
     // A position x is a gap iff (x >> gshift) == gx[j] for some j (gshift = log2 of the resolution multiple).
     int ngx, ngy, gshift;
     int gx[7], gy[7];
+    // shared-memory plan chosen by the host (conv_launch.cu): weights either stream with the activations (one B block
+    // per stage) or, when the whole layer fits, stay resident for the CTA's lifetime and only activations stream.
+    int wres;         // 1: weights resident (nchunks * kBStage bytes at the start of smem)
+    int nstages;      // pipeline stages in use (<= kMaxStages)
+    int stage_bytes;  // kAStage (+ kBStage when streaming weights)
     long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 
@@ -66,6 +71,7 @@ constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
 constexpr int next_pow2_c(int x) { int p = 32; while (p < x) p *= 2; return p; }
 
 constexpr int kEpiWarps = 8;
+constexpr int kMaxStages = 6;
 constexpr int kMmaWarps = 2;  // two issuers ping-pong pipeline stages (see the MMA section)
 constexpr int kConvThreads = (kEpiWarps + 1 + kMmaWarps) * 32;
 
@@ -143,24 +149,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     using T = ConvTraits<N, TH, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t s_bars[2 * T::kStages + 4];
+    __shared__ uint64_t s_bars[2 * kMaxStages + 5];
     __shared__ uint32_t s_tmem_slot;
     __shared__ __align__(16) float s_bias[N];
     __shared__ __align__(16) float s_neg[N];  // multiplier of the negative part: 1 / slope / PReLU weight
     uint64_t* full = s_bars;
-    uint64_t* empty = full + T::kStages;
-    uint64_t* tfull = empty + T::kStages;
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tfull = empty + kMaxStages;
     uint64_t* tempty = tfull + 2;
+    uint64_t* wfull = tempty + 2;  // resident weights landed
+    const int nstages = a.nstages;
+    uint8_t* stage0 = smem + (a.wres ? a.nchunks * T::kBStage : 0);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const long long t_start = clock64();
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < T::kStages; ++i) {
+        for (int i = 0; i < kMaxStages; ++i) {
             ptx::mbar_init(&full[i], 1);
             ptx::mbar_init(&empty[i], 1);
         }
+        ptx::mbar_init(wfull, 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull[i], kMmaWarps);  // every issuer commits its own MMAs of the tile
             ptx::mbar_init(&tempty[i], kEpiWarps);
@@ -184,6 +194,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_slot;
     const int num_tiles = a.tiles_x * a.tiles_y;
+    if (a.wres && warp == kEpiWarps && lane == 0) {
+        // weights are never written by a kernel: fetch them before waiting on the previous layer
+        ptx::mbar_expect_tx(wfull, a.nchunks * T::kBBytes);
+        for (int c = 0; c < a.nchunks; ++c)
+            ptx::bulk_load(smem + c * T::kBStage, a.wpack + static_cast<size_t>(c) * 9 * N * KC, T::kBBytes, wfull);
+    }
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, bias table; weights and bias are
     // never written by a kernel) overlaps the previous layer's tail. The next layer may start launching now; this
     // layer's activations / residuals are only touched after the previous grid has completed and flushed.
@@ -200,18 +216,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 const int x0 = tx * 128, y0 = a.y_begin + ty * TH;
                 for (int c = 0; c < a.nchunks; ++c) {
                     ptx::mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* st = smem + s * T::kStageBytes;
+                    uint8_t* st = stage0 + s * a.stage_bytes;
                     if (a.flags & FLAG_SKIP_TMA) {
                         ptx::mbar_arrive(&full[s]);
                     } else {
-                        const bool ld_a = !(a.flags & FLAG_SKIP_A), ld_b = !(a.flags & FLAG_SKIP_B);
+                        const bool ld_a = !(a.flags & FLAG_SKIP_A), ld_b = !(a.flags & FLAG_SKIP_B) && !a.wres;
                         ptx::mbar_expect_tx(&full[s], (ld_a ? T::kCopyBytes : 0) + (ld_b ? T::kBBytes : 0));
                         if (ld_a) ptx::tma_load_4d(st, &tmap, &full[s], a.cin_off + c * KC, x0 - 1, y0 - 1, 0);
                         if (ld_b)
                             ptx::bulk_load(st + T::kAStage, a.wpack + static_cast<size_t>(c) * 9 * N * KC, T::kBBytes,
                                            &full[s]);
                     }
-                    if (++s == T::kStages) { s = 0; ph ^= 1; }
+                    if (++s == nstages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -226,6 +242,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         // issue order stays deterministic (~320 cycles lost per stage; polling the next barrier mid-stage from a single
         // issuer was tried and is slower).
         const int mw = warp - (kEpiWarps + 1);  // 0 or 1
+        if (a.wres) ptx::mbar_wait(wfull, 0);
         int gstage = 0;                         // global stage counter over all tiles of this CTA
         // dy-stacked N: for an input row rho the three taps dy contribute to the three output rows r = rho - dy,
         // whose accumulators are ADJACENT TMEM column blocks. With the weights of (dy = 2, 1, 0) stored as
@@ -250,8 +267,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                     if (gstage > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
                 }
                 if (mine && ptx::elect_one()) {
-                    const uint32_t a_lo0 = (ptx::smem_u32(smem + s * T::kStageBytes) >> 4);
-                    const uint32_t b_lo0 = a_lo0 + (T::kAStage >> 4);
+                    const uint32_t a_lo0 = (ptx::smem_u32(stage0 + s * a.stage_bytes) >> 4);
+                    const uint32_t b_lo0 = a.wres ? (ptx::smem_u32(smem + c * T::kBStage) >> 4) : a_lo0 + (T::kAStage >> 4);
                     if (!skip_mma) {
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
@@ -293,7 +310,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 __syncwarp();
                 if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");  // other warp may issue next
                 ++gstage;
-                if (++s == T::kStages) { s = 0; ph ^= 1; }
+                if (++s == nstages) { s = 0; ph ^= 1; }
             }
             // this warp's MMAs of the tile are all issued: its commit is one of the kMmaWarps arrivals on tfull
             if (ptx::elect_one()) ptx::umma_commit(&tfull[buf]);
@@ -308,7 +325,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         // activation mode for bias_act: 0 identity, 1 max-form LeakyReLU, 2 general
         const int amode = a.act == ACT_NONE ? 0 : ((a.act == ACT_LRELU && a.slope >= 0.f && a.slope <= 1.f) ? 1 : 2);
         const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
-        uint8_t* stg = smem + T::kStages * T::kStageBytes + warp * T::kStgWarp;
+        uint8_t* stg = stage0 + nstages * a.stage_bytes + warp * T::kStgWarp;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;

@@ -4,6 +4,7 @@
 #include "conv3x3_sm100.cuh"
 #include "vr_common.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,6 +36,7 @@ struct ScopedDev {
             return;
         }
         dev.sm_count = p.multiProcessorCount;
+        if (const char* e = std::getenv("VR_WRES")) dev.weights_resident = std::atoi(e) != 0;
         if (cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking) != cudaSuccess) {
             set_error(&err, "cudaStreamCreate failed");
             return;

@@ -69,6 +69,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     std::string* err = nullptr;
     int64_t launches = 0;
+    bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc)
     std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
