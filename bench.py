@@ -300,6 +300,12 @@ def main():
         return 0
 
     peaks = load_peaks()
+    k1_traffic = {}
+    tp = ROOT / "profiles" / "k1_traffic.json"   # from the committed ncu capture (per-launch dram bytes of K1)
+    if tp.exists():
+        k1_traffic = json.loads(tp.read_text())
+    from video_restore_b200.models import MODEL_ZOO, conv_layers
+    n_conv_launches = len(conv_layers(MODEL_ZOO[wl["model"]])) + (1 if MODEL_ZOO[wl["model"]]["kind"] == "rrdb" else 0)
     fps = world * K / (dev_ms / 1e3)
     e2e_fps = world * K / (e2e_ms / 1e3)
     conv_tflops = executed / (conv_ms_1 / 1e3) / 1e12
@@ -315,7 +321,10 @@ def main():
                      "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["sustained"],
                      "peak_burst": peaks["burst"], "frac_of_burst": conv_tflops / peaks["burst"],
                      "peak_source": peaks["source"] + " (sustained figure: kernel timed inside a long step)",
-                     "traffic": None,
+                     "traffic": k1_traffic.get("dram_bytes_per_launch"), "traffic_source": k1_traffic.get("source"),
+                     "launches_per_step": n_conv_launches,
+                     "algorithmic_flop_per_launch": executed / max(n_conv_launches, 1),
+                     "avg_launch_us": conv_ms_1 * 1e3 / max(n_conv_launches, 1),
                      "conv_ms_per_step": conv_ms_1, "step_ms": total_ms_1,
                      "useful_tflops_whole_step": useful / (dev_ms / K / 1e3) / 1e12,
                      "useful_frac_of_sustained": useful / (dev_ms / K / 1e3) / 1e12 / peaks["sustained"]},
