@@ -290,3 +290,31 @@ def test_full_size_720p_x4plus_runs_and_is_tile_consistent(gpu_lib):
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     assert a.shape == (2880, 5120, 3) and d.max() <= 1 and (d > 0).mean() < 5e-3
     assert a.std() > 2.0
+
+
+def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
+    """Scheduling variants of the conv stack (read from the environment at handle creation) must not change a single
+    bit: multi-layer persistent launch (tile-row dependency counters), no PDL, streamed instead of resident weights,
+    and row-band scheduling."""
+    from video_restore_b200.restorer import FrameRestorer
+
+    name = "RealESRGAN_x4plus_anime_6B"
+    sd = random_state_dict(name, seed=0)
+    f = synth_frame(200, 300, seed=17)
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = FrameRestorer(name, sd, tile=128, tile_pad=16)     # 2x3 tiles -> atlas with gap rows and columns
+        out = r.process_frame(f)
+        n = r.launch_count
+        r.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        return out, n
+
+    base, n_base = run({})
+    multi, n_multi = run({"VR_MULTI": "1"})
+    assert np.array_equal(base, multi) and n_multi < n_base
+    assert np.array_equal(base, run({"VR_PDL": "0"})[0])
+    assert np.array_equal(base, run({"VR_WRES": "0"})[0])

@@ -225,6 +225,33 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
             // recomputed by the neighbouring band with identical values).
             for (int b0 = 0; b0 < nh; b0 += band) {
                 const int b1 = std::min(b0 + band, nh);
+                if (h->dev.multi_layer && band >= nh) {
+                    // conv1..conv4 in ONE persistent launch: tiles of conv_{k+1} start as soon as the rows of conv_k
+                    // they read are complete (no wave tail / pipeline refill between the four layers)
+                    ConvCall mc;
+                    mc.in = X.p;
+                    mc.in_cstride = X.c;
+                    mc.H = nh;
+                    mc.W = nw;
+                    mc.act = ACT_LRELU;
+                    mc.slope = 0.2f;
+                    mc.out = X.p;
+                    mc.out_cstride = X.c;
+                    mc.nlayers = 4;
+                    for (int k = 1; k <= 4; ++k) {
+                        mc.lw[k - 1] = layer(h, pre + std::to_string(k));
+                        if (!mc.lw[k - 1]) return fail(h, VR_E_STATE, "missing layer " + pre + std::to_string(k));
+                        mc.l_out_coff[k - 1] = 64 + 32 * (k - 1);
+                    }
+                    mc.ngx = h->gaps.ngx;
+                    mc.ngy = h->gaps.ngy;
+                    mc.gshift = h->gap_shift;
+                    for (int i = 0; i < 7; ++i) {
+                        mc.gx[i] = h->gaps.gx[i];
+                        mc.gy[i] = h->gaps.gy[i];
+                    }
+                    VR_TRY(run_conv(h->dev, mc));
+                } else
                 for (int k = 1; k <= 4; ++k) {
                     const Rows rr{std::max(b0 - (5 - k), 0), std::min(b1 + (5 - k), nh)};
                     VR_TRY(conv(h, pre + std::to_string(k), X, nh, nw, X, 64 + 32 * (k - 1), ACT_LRELU, nullptr, 0, 1.f,
@@ -519,6 +546,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     h->dev.err = &h->err;
     if (const char* e = std::getenv("VR_PDL")) h->dev.use_pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_WRES")) h->dev.weights_resident = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->dev.stream, cudaStreamNonBlocking) != cudaSuccess)
         return bad("cudaStreamCreate failed", VR_E_CUDA);

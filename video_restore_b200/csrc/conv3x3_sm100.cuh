@@ -29,6 +29,7 @@ namespace vr {
 enum ConvAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2 };
 enum ConvOut { OUT_NHWC = 0, OUT_RGB4 = 1, OUT_PS4 = 2 };
 // debug ablation flags (ConvArgs::flags): measurement only
+constexpr int kMaxLayers = 4;
 enum ConvFlags { FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8, FLAG_SKIP_B = 16, FLAG_SKIP_A = 32 };
 
 struct ConvArgs {
@@ -64,6 +65,17 @@ struct ConvArgs {
     int wres;         // 1: weights resident (nchunks * kBStage bytes at the start of smem)
     int nstages;      // pipeline stages in use (<= kMaxStages)
     int stage_bytes;  // kAStage (+ kBStage when streaming weights)
+    // Multi-layer launch (nlayers > 1): layers l = 0..nlayers-1 read the SAME source tensor (growing channel prefix of a
+    // dense block) and differ only in the fields below; work items are (layer, tile) in layer-major order and a tile of
+    // layer l waits until the tile rows of layer l-1 it reads are complete (dep counters, one int per layer and tile row).
+    int nlayers;
+    int l_nchunks[kMaxLayers];
+    const __half* l_wpack[kMaxLayers];
+    const float* l_bias[kMaxLayers];
+    int l_out_coff[kMaxLayers];
+    int* dep;         // [nlayers][tiles_y], zero on entry
+    int* dep_zero;    // the other launch parity's region: zeroed by this launch for the next multi-layer launch
+    int dep_zero_n;
     long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 
@@ -88,7 +100,7 @@ struct ConvTraits {
     static constexpr int kBBytes = 9 * N * kRowBytes;
     static constexpr int kBStage = round_up_c(kBBytes, 1024);
     static constexpr int kStageBytes = kAStage + kBStage;
-    static constexpr int kStatic = 1024;  // static __shared__: barriers, tmem slot, bias / activation tables
+    static constexpr int kStatic = 2048;  // static __shared__: barriers, tmem slot, per-layer bias / activation tables
     // per-warp epilogue staging (NHWC outputs only): 32 pixels x (N fp16 + 16 B pad) for the coalescing transpose
     static constexpr int kStgPitch = N * 2 + 16;
     static constexpr int kStgWarp = (N % 32 == 0) ? 32 * kStgPitch : 0;
@@ -151,8 +163,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t s_bars[2 * kMaxStages + 5];
     __shared__ uint32_t s_tmem_slot;
-    __shared__ __align__(16) float s_bias[N];
+    __shared__ __align__(16) float s_bias_all[kMaxLayers][N];
     __shared__ __align__(16) float s_neg[N];  // multiplier of the negative part: 1 / slope / PReLU weight
+    __shared__ int s_l_nchunks[kMaxLayers], s_l_out_coff[kMaxLayers];
+    __shared__ const __half* s_l_wpack[kMaxLayers];
     uint64_t* full = s_bars;
     uint64_t* empty = full + kMaxStages;
     uint64_t* tfull = empty + kMaxStages;
@@ -182,8 +196,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         __syncwarp();
         ptx::tmem_alloc<T::kTmemCols>(&s_tmem_slot);
     }
+    if (threadIdx.x < kMaxLayers) {
+        const int l = threadIdx.x;
+        const bool multi = a.nlayers > 1;
+        s_l_nchunks[l] = multi ? a.l_nchunks[l] : a.nchunks;
+        s_l_out_coff[l] = multi ? a.l_out_coff[l] : a.out_coff;
+        s_l_wpack[l] = multi ? a.l_wpack[l] : a.wpack;
+    }
+    for (int i = threadIdx.x; i < N * kMaxLayers; i += blockDim.x) {
+        const int l = i / N, ch = i - l * N;
+        const float* bp = a.nlayers > 1 ? (l < a.nlayers ? a.l_bias[l] : nullptr) : a.bias;
+        s_bias_all[l][ch] = (ch < a.cout && bp) ? bp[ch] : 0.f;
+    }
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        s_bias[i] = (i < a.cout && a.bias) ? a.bias[i] : 0.f;
         float neg = 1.f;
         if (a.act == ACT_LRELU) neg = a.slope;
         if (a.act == ACT_PRELU) neg = (i < a.cout && a.prelu) ? a.prelu[i] : 0.f;
@@ -194,6 +219,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_slot;
     const int num_tiles = a.tiles_x * a.tiles_y;
+    const int num_items = num_tiles * a.nlayers;
     if (a.wres && warp == kEpiWarps && lane == 0) {
         // weights are never written by a kernel: fetch them before waiting on the previous layer
         ptx::mbar_expect_tx(wfull, a.nchunks * T::kBBytes);
@@ -205,16 +231,62 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     // layer's activations / residuals are only touched after the previous grid has completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a.dep_zero && blockIdx.x == 0 && warp == 0)
+        for (int i = lane; i < a.dep_zero_n; i += 32) a.dep_zero[i] = 0;
 
     if (warp == kEpiWarps) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int pre0 = 0, pre1 = 0, pre2 = 0;
+            bool pre_valid = false;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int layer = item / num_tiles, tile = item - layer * num_tiles;
                 const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
                 const int x0 = tx * 128, y0 = a.y_begin + ty * TH;
-                for (int c = 0; c < a.nchunks; ++c) {
+                const int nch = s_l_nchunks[layer];
+                const __half* wp = s_l_wpack[layer];
+                if (layer > 0) {
+                    // rows y0-1 .. y0+TH of the previous layer = its tile rows ty-1 .. ty+1, all tile columns.
+                    // The three counters were read one item ahead (pre0..2, below): normally no round trip here.
+                    const int target = a.tiles_x * kEpiWarps;
+                    const int r0 = ty > 0 ? ty - 1 : 0, r1 = ty + 1 < a.tiles_y ? ty + 1 : a.tiles_y - 1;
+                    const int rm = r0 + 1 <= r1 ? r0 + 1 : r1;
+                    const int* ctr = a.dep + (layer - 1) * a.tiles_y;
+                    if (!(pre_valid && pre0 >= target && pre1 >= target && pre2 >= target)) {
+                        const long long tw = clock64();
+                        for (;;) {
+                            int v0, v1, v2;
+                            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v0) : "l"(ctr + r0) : "memory");
+                            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v1) : "l"(ctr + rm) : "memory");
+                            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v2) : "l"(ctr + r1) : "memory");
+                            if (v0 >= target && v1 >= target && v2 >= target) break;
+                            if (clock64() - tw > 4000000000LL) __trap();
+                        }
+                    }
+                    // the rows were written with generic-proxy stores by other CTAs; TMA reads through the async proxy
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                pre_valid = false;
+                {
+                    // read the NEXT item's dependency counters now; their latency hides behind this item's loads
+                    const int nitem = item + static_cast<int>(gridDim.x);
+                    if (nitem < num_items) {
+                        const int nl = nitem / num_tiles, nt = nitem - nl * num_tiles;
+                        if (nl > 0) {
+                            const int nty = nt / a.tiles_x;
+                            const int r0 = nty > 0 ? nty - 1 : 0, r1 = nty + 1 < a.tiles_y ? nty + 1 : a.tiles_y - 1;
+                            const int rm = r0 + 1 <= r1 ? r0 + 1 : r1;
+                            const int* ctr = a.dep + (nl - 1) * a.tiles_y;
+                            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(pre0) : "l"(ctr + r0) : "memory");
+                            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(pre1) : "l"(ctr + rm) : "memory");
+                            asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(pre2) : "l"(ctr + r1) : "memory");
+                            pre_valid = true;
+                        }
+                    }
+                }
+                for (int c = 0; c < nch; ++c) {
                     ptx::mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = stage0 + s * a.stage_bytes;
                     if (a.flags & FLAG_SKIP_TMA) {
@@ -224,8 +296,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                         ptx::mbar_expect_tx(&full[s], (ld_a ? T::kCopyBytes : 0) + (ld_b ? T::kBBytes : 0));
                         if (ld_a) ptx::tma_load_4d(st, &tmap, &full[s], a.cin_off + c * KC, x0 - 1, y0 - 1, 0);
                         if (ld_b)
-                            ptx::bulk_load(st + T::kAStage, a.wpack + static_cast<size_t>(c) * 9 * N * KC, T::kBBytes,
-                                           &full[s]);
+                            ptx::bulk_load(st + T::kAStage, wp + static_cast<size_t>(c) * 9 * N * KC, T::kBBytes, &full[s]);
                     }
                     if (++s == nstages) { s = 0; ph ^= 1; }
                 }
@@ -251,13 +322,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         int s = 0;
         uint32_t ph = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t aph = (it >> 1) & 1;
+            const int nch = s_l_nchunks[item / num_tiles];
             ptx::mbar_wait(&tempty[buf], aph ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_base = tmem_base + buf * T::kAccCols;
-            for (int c = 0; c < a.nchunks; ++c) {
+            for (int c = 0; c < nch; ++c) {
                 const bool mine = (gstage & 1) == mw;
                 if (mine) {
                     ptx::mbar_wait(&full[s], ph);
@@ -327,9 +399,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
         uint8_t* stg = stage0 + nstages * a.stage_bytes + warp * T::kStgWarp;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t aph = (it >> 1) & 1;
+            const int layer = item / num_tiles, tile = item - layer * num_tiles;
+            const int out_coff = s_l_out_coff[layer];
+            const float* s_bias = s_bias_all[layer];
             const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
             const int x = tx * 128 + quarter * 32 + lane;
             const int y0 = a.y_begin + ty * TH;
@@ -443,7 +518,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                         // coalesced write-out: consecutive lanes write consecutive 16 B units of the same pixel
                         constexpr int kUnits = N / 8;  // 16 B units per pixel
                         const int x_base = tx * 128 + quarter * 32;
-                        __half* orow = a.out + (static_cast<size_t>(y) * a.W + x_base) * a.out_cstride + a.out_coff;
+                        __half* orow = a.out + (static_cast<size_t>(y) * a.W + x_base) * a.out_cstride + out_coff;
 #pragma unroll
                         for (int i = 0; i < kUnits; ++i) {
                             const int idx = i * 32 + lane;
@@ -459,7 +534,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty[buf]);
+            if (lane == 0) ptx::mbar_arrive(&tempty[buf]);  // TMEM buffer is free as soon as it has been read
+            if (layer + 1 < a.nlayers) {
+                __threadfence();  // every lane: this tile's rows are visible device-wide before the row counter moves
+                __syncwarp();
+                if (lane == 0) atomicAdd(a.dep + layer * a.tiles_y + ty, 1);
+            }
         }
     }
 

@@ -156,13 +156,13 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     }
     a.tiles_x = (a.W + 127) / 128;
     a.tiles_y = (a.y_end - a.y_begin + TH - 1) / TH;
-    const int tiles = a.tiles_x * a.tiles_y;
+    const int tiles = a.tiles_x * a.tiles_y * a.nlayers;  // work items of this launch
     const int grid = tiles < dev.sm_count ? tiles : dev.sm_count;
     // shared-memory plan: resident weights when the whole layer fits WITHOUT reducing the pipeline depth (measured:
     // +3..5 % on 64->32, 96->32, 64->64; with only 2 activation stages left, 128->32 / 160->32 lose 4..8 %)
     const int w_bytes = a.nchunks * T::kBStage;
     const int a_stages = (T::kBudget - w_bytes) / T::kAStage;
-    if (dev.weights_resident && a_stages >= T::kStages) {
+    if (dev.weights_resident && a.nlayers == 1 && a_stages >= T::kStages) {
         a.wres = 1;
         a.nstages = a_stages > kMaxStages ? kMaxStages : a_stages;
         a.stage_bytes = T::kAStage;
@@ -188,10 +188,18 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
 }
 
 int run_conv(Device& dev, const ConvCall& c) {
-    const ConvWeights& w = *c.w;
-    if (c.in_cstride % 8 != 0 || c.cin_off % 8 != 0 || c.cin_off + w.nchunks * w.kc > c.in_cstride) {
-        set_error(dev.err, "run_conv: input channel slice not addressable (cstride/offset/chunks)");
-        return -1;
+    const ConvWeights& w = c.nlayers > 1 ? *c.lw[c.nlayers - 1] : *c.w;  // the layer with the widest channel prefix
+    if (c.nlayers > 1) {
+        if (c.nlayers > kMaxLayers || c.out_mode != OUT_NHWC || c.res1 || c.res2) {
+            set_error(dev.err, "run_conv: unsupported multi-layer call");
+            return -1;
+        }
+        for (int l = 0; l < c.nlayers; ++l)
+            if (!c.lw[l] || c.lw[l]->npad != w.npad || c.lw[l]->kc != w.kc || c.lw[l]->cout != w.cout ||
+                c.lw[l]->nchunks > w.nchunks || c.l_out_coff[l] % 8 != 0) {
+                set_error(dev.err, "run_conv: multi-layer launch needs layers of one shape family");
+                return -1;
+            }
     }
     int rows = c.rows;
     if (rows == 0) rows = 4;
@@ -229,6 +237,28 @@ int run_conv(Device& dev, const ConvCall& c) {
     a.base_cstride = c.base_cstride;
     a.flags = c.flags;
     a.dbg_cycles = c.dbg_cycles;
+    a.nlayers = c.nlayers;
+    if (c.nlayers > 1) {
+        for (int l = 0; l < c.nlayers; ++l) {
+            a.l_nchunks[l] = c.lw[l]->nchunks;
+            a.l_wpack[l] = c.lw[l]->wpack;
+            a.l_bias[l] = c.lw[l]->bias;
+            a.l_out_coff[l] = c.l_out_coff[l];
+        }
+        if (!dev.dep_buf) {
+            VR_CUDA_CHECK(cudaMalloc(&dev.dep_buf, 2 * Device::kDepRegion * sizeof(int)), dev.err);
+            VR_CUDA_CHECK(cudaMemset(dev.dep_buf, 0, 2 * Device::kDepRegion * sizeof(int)), dev.err);
+        }
+        const int th = rows, tiles_y = ((a.y_end - a.y_begin) + th - 1) / th;
+        if (c.nlayers * tiles_y > Device::kDepRegion) {
+            set_error(dev.err, "run_conv: image too tall for the dependency counter region");
+            return -1;
+        }
+        a.dep = dev.dep_buf + dev.dep_parity * Device::kDepRegion;
+        a.dep_zero = dev.dep_buf + (dev.dep_parity ^ 1) * Device::kDepRegion;
+        a.dep_zero_n = Device::kDepRegion;
+        dev.dep_parity ^= 1;
+    }
     a.ngx = c.ngx;
     a.ngy = c.ngy;
     a.gshift = c.gshift;

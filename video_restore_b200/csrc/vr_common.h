@@ -61,6 +61,11 @@ struct ConvCall {
     int gx[7] = {0}, gy[7] = {0};
     int flags = 0;  // ConvFlags (debug ablations)
     long long* dbg_cycles = nullptr;
+    // multi-layer launch: layers 0..nlayers-1 share `in` (growing channel prefix) and `out`; per layer: weights and the
+    // output channel offset. nlayers == 1: the scalar fields above describe the layer.
+    int nlayers = 1;
+    const ConvWeights* lw[4] = {nullptr, nullptr, nullptr, nullptr};
+    int l_out_coff[4] = {0, 0, 0, 0};
 };
 
 struct Device {
@@ -69,6 +74,14 @@ struct Device {
     cudaStream_t stream = nullptr;
     std::string* err = nullptr;
     int64_t launches = 0;
+    // dependency counters of multi-layer launches: two regions used alternately (each launch zeroes the other one)
+    int* dep_buf = nullptr;
+    int dep_parity = 0;
+    static constexpr int kDepRegion = 4 * 4096;
+    // VR_MULTI=1: conv1..conv4 of a dense block in one persistent launch with tile-row dependency counters. Bit-identical;
+    // measured +1 % (720p single tile) / -2.7 % (6-tile atlas: resident weights are lost, little wave tail to recover),
+    // so off by default. Kept as the base of the per-RDB persistent kernel.
+    bool multi_layer = false;
     bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc)
