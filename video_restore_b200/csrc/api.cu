@@ -143,7 +143,8 @@ struct Rows {  // output row range of one launch (row-band scheduling); default 
 
 int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act,
          const __half* res1 = nullptr, int res1_c = 0, float s1 = 1.f, const __half* res2 = nullptr, int res2_c = 0,
-         float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr, int base_c = 0, Rows rows = Rows()) {
+         float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr, int base_c = 0, Rows rows = Rows(),
+         int phase = -1) {
     const ConvWeights* w = layer(h, name);
     if (!w) return fail(h, VR_E_STATE, "missing layer " + name);
     ConvCall c;
@@ -168,6 +169,14 @@ int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out,
     c.base_cstride = base_c;
     c.y_begin = rows.y0;
     c.y_end = rows.y1;
+    if (phase >= 0) {  // output phase (py, px) of a conv folded with a preceding nearest x2 upsample
+        const int py = phase >> 1, px = phase & 1;
+        c.dys = py == 0 ? 1 : 2;  // py = 0 reads rows y-1, y (taps 0,1); py = 1 reads rows y, y+1 (taps 1,2)
+        c.dxs = px == 0 ? 1 : 2;
+        c.omul = 2;
+        c.opy = py;
+        c.opx = px;
+    }
     c.ngx = h->gaps.ngx;
     c.ngy = h->gaps.ngy;
     c.gshift = h->gap_shift;
@@ -202,7 +211,7 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
     VR_TRY(ensure(h, h->feat, px * 64 * 2));
     VR_TRY(ensure(h, h->trunk, px * 64 * 2));
     for (int i = 0; i < 3; ++i) VR_TRY(ensure(h, h->rdb[i], px * 192 * 2));
-    VR_TRY(ensure(h, h->up1_in, px * 4 * 64 * 2));
+    if (!h->dev.fold_upsample) VR_TRY(ensure(h, h->up1_in, px * 4 * 64 * 2));
     VR_TRY(ensure(h, h->up1_out, px * 4 * 64 * 2));
     VR_TRY(ensure(h, h->up2_in, px * 16 * 64 * 2));
     VR_TRY(ensure(h, h->up2_out, px * 16 * 64 * 2));
@@ -272,12 +281,25 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
     VR_TRY(conv(h, "conv_body", rdb[0], nh, nw, trunk, 0, ACT_NONE, feat.p, 64, 1.0f));  // feat + body_feat
     Act u1i{static_cast<__half*>(h->up1_in.p), 64}, u1o{static_cast<__half*>(h->up1_out.p), 64};
     Act u2i{static_cast<__half*>(h->up2_in.p), 64}, u2o{static_cast<__half*>(h->up2_out.p), 64};
-    VR_TRY(launch_upsample2x(h->dev, trunk.p, nh, nw, 64, u1i.p));
-    h->gap_shift = 1;  // gap columns / rows are 2 pixels wide at 2x, 4 at 4x (nearest upsampling keeps them zero)
-    VR_TRY(conv(h, "conv_up1", u1i, 2 * nh, 2 * nw, u1o, 0, ACT_LRELU));
-    VR_TRY(launch_upsample2x(h->dev, u1o.p, 2 * nh, 2 * nw, 64, u2i.p));
-    h->gap_shift = 2;
-    VR_TRY(conv(h, "conv_up2", u2i, 4 * nh, 4 * nw, u2o, 0, ACT_LRELU));
+    if (h->dev.fold_upsample) {
+        // lrelu(conv_up(nearest_x2(f))) as four 2x2-tap convs on f itself (one per output phase, pre-summed weights):
+        // no upsampled tensor, 4/9 of the MACs
+        for (int ph = 0; ph < 4; ++ph)
+            VR_TRY(conv(h, "conv_up1.phase" + std::to_string(ph), trunk, nh, nw, u1o, 0, ACT_LRELU, nullptr, 0, 1.f,
+                        nullptr, 0, 1.f, OUT_NHWC, nullptr, 0, Rows(), ph));
+        h->gap_shift = 1;  // the phases of conv_up2 run on the 2x grid: gap columns / rows are 2 pixels wide there
+        for (int ph = 0; ph < 4; ++ph)
+            VR_TRY(conv(h, "conv_up2.phase" + std::to_string(ph), u1o, 2 * nh, 2 * nw, u2o, 0, ACT_LRELU, nullptr, 0, 1.f,
+                        nullptr, 0, 1.f, OUT_NHWC, nullptr, 0, Rows(), ph));
+        h->gap_shift = 2;
+    } else {
+        VR_TRY(launch_upsample2x(h->dev, trunk.p, nh, nw, 64, u1i.p));
+        h->gap_shift = 1;  // gap columns / rows are 2 pixels wide at 2x, 4 at 4x (nearest upsampling keeps them zero)
+        VR_TRY(conv(h, "conv_up1", u1i, 2 * nh, 2 * nw, u1o, 0, ACT_LRELU));
+        VR_TRY(launch_upsample2x(h->dev, u1o.p, 2 * nh, 2 * nw, 64, u2i.p));
+        h->gap_shift = 2;
+        VR_TRY(conv(h, "conv_up2", u2i, 4 * nh, 4 * nw, u2o, 0, ACT_LRELU));
+    }
     VR_TRY(conv(h, "conv_hr", u2o, 4 * nh, 4 * nw, u2i, 0, ACT_LRELU));  // up2_in is dead: reuse for conv_hr out
     Act to{tile_out, 4};
     VR_TRY(conv(h, "conv_last", u2i, 4 * nh, 4 * nw, to, 0, ACT_NONE, nullptr, 0, 1.f, nullptr, 0, 1.f, OUT_RGB4));
@@ -547,6 +569,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     if (const char* e = std::getenv("VR_PDL")) h->dev.use_pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_WRES")) h->dev.weights_resident = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->dev.stream, cudaStreamNonBlocking) != cudaSuccess)
         return bad("cudaStreamCreate failed", VR_E_CUDA);
@@ -639,6 +662,23 @@ int vr_commit_weights(vr_handle* h) {
         ConvWeights cw;
         VR_TRY(pack_conv_weights(h->dev, w.data.data(), bi->second.data.data(), prelu, s.cin, s.cout, &cw));
         h->layers[s.name] = cw;
+        if (s.name == "conv_up1" || s.name == "conv_up2") {
+            // conv3x3(nearest_x2(f)) at output (2y+py, 2x+px) reads f rows {y-1, y} (py = 0) or {y, y+1} (py = 1): the
+            // three original row taps collapse onto two source rows, E_py[0] = W[0], E_py[1] = W[1] + W[2] (py = 0) /
+            // E_py[1] = W[0] + W[1], E_py[2] = W[2] (py = 1); same for columns. Summed in fp32, rounded to fp16 once.
+            for (int ph = 0; ph < 4; ++ph) {
+                const int py = ph >> 1, pxp = ph & 1;
+                std::vector<float> e(w.data.size(), 0.f);
+                auto tgt = [](int p, int t) { return p == 0 ? (t == 0 ? 0 : 1) : (t == 2 ? 2 : 1); };
+                for (size_t oc = 0; oc < static_cast<size_t>(s.cout) * s.cin; ++oc)
+                    for (int dy = 0; dy < 3; ++dy)
+                        for (int dx = 0; dx < 3; ++dx)
+                            e[oc * 9 + tgt(py, dy) * 3 + tgt(pxp, dx)] += w.data[oc * 9 + dy * 3 + dx];
+                ConvWeights pw;
+                VR_TRY(pack_conv_weights(h->dev, e.data(), bi->second.data.data(), nullptr, s.cin, s.cout, &pw));
+                h->layers[s.name + ".phase" + std::to_string(ph)] = pw;
+            }
+        }
     }
     h->raw.clear();
     h->committed = true;

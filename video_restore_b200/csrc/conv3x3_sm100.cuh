@@ -55,6 +55,9 @@ struct ConvArgs {
     const __half* base;  // OUT_PS4: network input (RGB in channels 0..2), added to the 16 sub-pixels
     int base_cstride;
     int flags;  // ConvFlags
+    // output pixel mapping (NHWC): output (y, x) is stored at row y*omul + opy, column x*omul + opx of an image omul times
+    // as wide. omul = 2 writes one phase of a conv that was folded with a preceding nearest x2 upsample.
+    int omul, opy, opx;
     // Tile atlas: several RealESRGANer tiles share one image, separated by zero gap columns / rows (the gap IS the
     // per-tile zero padding). Outputs at gap positions are forced to zero so the separation survives every layer.
     // A position x is a gap iff (x >> gshift) == gx[j] for some j (gshift = log2 of the resolution multiple).
@@ -155,9 +158,13 @@ __device__ __forceinline__ void bias_act(float* v, const float* s_bias, const fl
     }
 }
 
-template <int N, int TH, int KC>
+// DYS / DXS select the taps that are present: 0 = all three, 1 = {0, 1}, 2 = {1, 2} (the 2x2 sub-kernels of the four
+// output phases of upsample-then-conv; the absent taps have zero weights and their MMAs are simply not issued).
+template <int N, int TH, int KC, int DYS = 0, int DXS = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
+    constexpr int kDy0 = DYS == 2 ? 1 : 0, kDy1 = DYS == 1 ? 1 : 2;  // present dy taps [kDy0, kDy1]
+    constexpr int kDx0 = DXS == 2 ? 1 : 0, kDx1 = DXS == 1 ? 1 : 2;
     using T = ConvTraits<N, TH, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -343,23 +350,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                     const uint32_t b_lo0 = a.wres ? (ptx::smem_u32(smem + c * T::kBStage) >> 4) : a_lo0 + (T::kAStage >> 4);
                     if (!skip_mma) {
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
+                        for (int dx = kDx0; dx <= kDx1; ++dx) {
 #pragma unroll
                             for (int k = 0; k < T::kKSteps; ++k) {
 #pragma unroll
                                 for (int rho = 0; rho < T::kInRows; ++rho) {
                                     const uint32_t a_lo = a_lo0 + (((rho * T::kPitch + dx) * T::kRowBytes + k * 32) >> 4);
                                     constexpr int kLast = TH - 1;
-                                    const int dy_lo = rho - kLast > 0 ? rho - kLast : 0;
-                                    const int dy_hi = rho < 2 ? rho : 2;
+                                    // taps dy in [dy_lo, dy_hi] of this input row land in output rows rho - dy
+                                    const int lo_r = rho - kLast > 0 ? rho - kLast : 0;
+                                    const int hi_r = rho < 2 ? rho : 2;
+                                    const int dy_lo = lo_r > kDy0 ? lo_r : kDy0;
+                                    const int dy_hi = hi_r < kDy1 ? hi_r : kDy1;
+                                    if (dy_lo > dy_hi) continue;  // this input row feeds no present tap
                                     const int nblk = dy_hi - dy_lo + 1;
                                     const int r_lo = rho - dy_hi;
                                     // B rows of this dx: [dy=2 | dy=1 | dy=0] x N
                                     const uint32_t b_lo = b_lo0 + ((((dx * 3 + (2 - dy_hi)) * N) * T::kRowBytes + k * 32) >> 4);
                                     const uint32_t d = d_base + r_lo * N;
-                                    if (dx == 0 && k == 0 && dy_lo == 0 && c == 0) {
-                                        // the dy = 0 block is the first touch of output row rho in this tile:
-                                        // it must overwrite while the other blocks accumulate -> split the MMA
+                                    if (dx == kDx0 && k == 0 && dy_lo == kDy0 && c == 0) {
+                                        // the lowest present tap is the first touch of output row rho - kDy0 in this
+                                        // tile: it must overwrite while the other blocks accumulate -> split the MMA
                                         if (nblk > 1)
                                             ptx::umma_f16<ptx::kCollNone>(
                                                 d, a_lo, T::kDescHi, b_lo, T::kDescHi,
@@ -518,14 +529,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                         // coalesced write-out: consecutive lanes write consecutive 16 B units of the same pixel
                         constexpr int kUnits = N / 8;  // 16 B units per pixel
                         const int x_base = tx * 128 + quarter * 32;
-                        __half* orow = a.out + (static_cast<size_t>(y) * a.W + x_base) * a.out_cstride + out_coff;
+                        __half* orow = a.out + out_coff +
+                                       (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) *
+                                           a.out_cstride;
 #pragma unroll
                         for (int i = 0; i < kUnits; ++i) {
                             const int idx = i * 32 + lane;
                             const int px = idx / kUnits, un = idx % kUnits;
                             if (x_base + px < a.W) {
                                 const uint4 val = *reinterpret_cast<const uint4*>(stg + px * T::kStgPitch + un * 16);
-                                *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.out_cstride + un * 8) = val;
+                                *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
                             }
                         }
                         __syncwarp();

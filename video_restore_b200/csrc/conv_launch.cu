@@ -144,10 +144,10 @@ void free_conv_weights(ConvWeights* w) {
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
-template <int N, int TH, int KC>
+template <int N, int TH, int KC, int DYS = 0, int DXS = 0>
 static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     using T = ConvTraits<N, TH, KC>;
-    auto kern = conv3x3_tc_kernel<N, TH, KC>;
+    auto kern = conv3x3_tc_kernel<N, TH, KC, DYS, DXS>;
     static bool attr_done[64] = {};
     if (!attr_done[dev.ordinal & 63]) {
         VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kBudget + T::kStgBytes + 1024),
@@ -237,6 +237,9 @@ int run_conv(Device& dev, const ConvCall& c) {
     a.base_cstride = c.base_cstride;
     a.flags = c.flags;
     a.dbg_cycles = c.dbg_cycles;
+    a.omul = c.omul < 1 ? 1 : c.omul;
+    a.opy = c.opy;
+    a.opx = c.opx;
     a.nlayers = c.nlayers;
     if (c.nlayers > 1) {
         for (int l = 0; l < c.nlayers; ++l) {
@@ -273,6 +276,19 @@ int run_conv(Device& dev, const ConvCall& c) {
     if (c.out_mode == OUT_PS4 && w.npad != 48) {
         set_error(dev.err, "run_conv: pixel-shuffle output needs cout == 48");
         return -1;
+    }
+    if (c.dys || c.dxs) {
+        // 2x2-tap phases of an upsample-folded conv: only the 64-channel / 4-row / 32-channel-chunk family is built
+        if (w.npad != 64 || rows != 4 || w.kc != 32 || c.nlayers != 1 || c.dys < 1 || c.dys > 2 || c.dxs < 1 || c.dxs > 2) {
+            set_error(dev.err, "run_conv: no phase kernel for this layer shape");
+            return -1;
+        }
+        switch (c.dys * 10 + c.dxs) {
+            case 11: return launch_one<64, 4, 32, 1, 1>(dev, tm, a);
+            case 12: return launch_one<64, 4, 32, 1, 2>(dev, tm, a);
+            case 21: return launch_one<64, 4, 32, 2, 1>(dev, tm, a);
+            default: return launch_one<64, 4, 32, 2, 2>(dev, tm, a);
+        }
     }
     const int key = (w.npad * 100 + rows) * 100 + w.kc;
     switch (key) {

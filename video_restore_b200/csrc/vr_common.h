@@ -56,6 +56,9 @@ struct ConvCall {
     const __half* base = nullptr;
     int base_cstride = 0;
     int rows = 0;   // output rows per CTA tile (TH), 0 = default
+    // phase of an upsample-folded conv: taps present (0 all, 1 = {0,1}, 2 = {1,2}) and the output pixel mapping
+    int dys = 0, dxs = 0;
+    int omul = 1, opy = 0, opx = 0;
     // tile-atlas gap mask (see ConvArgs): gap columns / rows in units of (1 << gshift) pixels
     int ngx = 0, ngy = 0, gshift = 0;
     int gx[7] = {0}, gy[7] = {0};
@@ -82,6 +85,7 @@ struct Device {
     // measured +1 % (720p single tile) / -2.7 % (6-tile atlas: resident weights are lost, little wave tail to recover),
     // so off by default. Kept as the base of the per-RDB persistent kernel.
     bool multi_layer = false;
+    bool fold_upsample = true;     // VR_FOLD_UP=0: materialise nearest x2 and run conv_up1/2 as plain 3x3 convs
     bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc)
