@@ -7,7 +7,8 @@ One "step" = one frame through the whole hot path (bilateral -> tiled Real-ESRGA
 temporal). Default workload = BASELINE.json configs[3]: RealESRGAN_x4plus 720p -> 2880p, `--quality max --enhanced`
 preset of the reference CLI (tile 512, overlap 64, video_upscaler.py:690-691) with every enhancement on.
   value : frames/s with frames resident in HBM (vr_restore_device_async), CUDA events on the library's stream
-  e2e   : frames/s through FrameRestorer.process_frame with pinned HOST buffers (H2D + D2H inside the timed region)
+  e2e   : frames/s through FrameRestorer.process_stream with pinned HOST buffers (H2D + D2H of every frame inside the
+          timed region, overlapped with the compute of neighbouring frames)
   roofline : conv kernel (K1) -- executed conv FLOPs of the step / summed conv-kernel time, vs MEASURED_PEAKS.json
   cpu_baseline : the oracle (CPU fp32 restatement of the reference path) on this box's host cores, bounded sample
 `--impl reference` times only that CPU path (rank 0), printing the same metric.
@@ -227,7 +228,6 @@ def main():
     n_src = 4
     host_frames = [synth_frame(H, W, seed=11, index=rank * K + i) for i in range(n_src)]
     pinned_in = [torch.from_numpy(f).pin_memory() for f in host_frames]
-    pinned_out = torch.empty((H * s, W * s, 3), dtype=torch.uint8).pin_memory()
     d_in = [t.cuda(non_blocking=False) for t in pinned_in]
     d_out = torch.empty((H * s, W * s, 3), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.ExternalStream(r.stream)
@@ -272,15 +272,18 @@ def main():
     r.process_frame_device(d_in[0].data_ptr(), H, W, d_out.data_ptr(), opts, sync=True)
     total_ms_1, conv_ms_1 = r.last_timing()
 
-    # ---- end to end through the public API with pinned host buffers ----
-    out_np = pinned_out.numpy()
+    # ---- end to end through the public API: host frames in, host frames out ----
+    # FrameRestorer.process_stream (vr_submit / vr_wait): every frame is copied host -> device from pinned memory,
+    # restored, and copied device -> host into pinned memory, all inside the timed region; copies of neighbouring
+    # frames overlap the compute (two frames in flight). The consumer reads one pixel of every output frame.
     in_np = [t.numpy() for t in pinned_in]
-    for i in range(2):
-        r.process_frame(in_np[i % n_src], opts, out=out_np)
+    for _ in r.process_stream((in_np[i % n_src] for i in range(3)), opts):
+        pass
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
-        r.process_frame(in_np[i % n_src], opts, out=out_np)
+    checksum = 0
+    for out in r.process_stream((in_np[i % n_src] for i in range(K)), opts):
+        checksum += int(out[0, 0, 0])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()

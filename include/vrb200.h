@@ -94,6 +94,17 @@ int vr_restore_device_async(vr_handle* h, const uint8_t* d_bgr, int32_t H, int32
 int vr_sync(vr_handle* h);
 void* vr_stream(vr_handle* h); /* cudaStream_t the handle enqueues on */
 
+/* Pipelined host-buffer path: vr_submit enqueues H2D (copy stream) -> restore (compute stream) -> D2H (copy stream)
+ * for one frame and returns at once with a ticket; up to two frames are in flight, so the copies of neighbouring
+ * frames overlap the compute of the current one. bgr/out must stay valid (and should be pinned, see vr_host_alloc)
+ * until vr_wait(ticket) returns. Frames are processed in submission order (temporal state included). */
+int vr_submit(vr_handle* h, const uint8_t* bgr, int32_t H, int32_t W, int64_t stride, uint8_t* out,
+              int64_t out_stride, const vr_frame_opts* opts, int64_t* ticket);
+int vr_wait(vr_handle* h, int64_t ticket);
+/* Page-locked host memory for the frame buffers of vr_restore / vr_submit. */
+void* vr_host_alloc(size_t bytes);
+void vr_host_free(void* p);
+
 /* Temporal-consistency state: the previous frame's un-blended upscaled result ("up_{t-1}").
  * A frame-range shard seeds it with the boundary frame received from its left neighbour. */
 int vr_temporal_reset(vr_handle* h);

@@ -318,3 +318,19 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
     assert np.array_equal(base, multi) and n_multi < n_base
     assert np.array_equal(base, run({"VR_PDL": "0"})[0])
     assert np.array_equal(base, run({"VR_WRES": "0"})[0])
+
+
+def test_process_stream_equals_per_frame_calls(gpu_lib):
+    """Pipelined host path (vr_submit / vr_wait) == one synchronous vr_restore per frame, temporal state included."""
+    from video_restore_b200.restorer import FrameOpts
+
+    gpu, _ = _pair("RealESRGAN_x4_v3", 64, 10)
+    frames = [synth_frame(72, 100, seed=31, index=i) for i in range(7)]
+    opts = FrameOpts(denoise=True, sharpen=0.3, clahe=True, temporal=True)
+    ref = [gpu.process_frame(f, opts) for f in frames]
+    gpu.temporal_reset()
+    got = [o.copy() for o in gpu.process_stream(iter(frames), opts)]
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    gpu.close()

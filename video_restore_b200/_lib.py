@@ -59,6 +59,11 @@ SIGNATURES = {
                                     C.POINTER(VrFrameOpts)]),
     "vr_restore_device_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                           C.c_int64, C.POINTER(VrFrameOpts)]),
+    "vr_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
+                            C.POINTER(VrFrameOpts), C.POINTER(C.c_int64)]),
+    "vr_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "vr_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "vr_host_free": (None, [C.c_void_p]),
     "vr_sync": (C.c_int, [C.c_void_p]),
     "vr_stream": (C.c_void_p, [C.c_void_p]),
     "vr_temporal_reset": (C.c_int, [C.c_void_p]),
@@ -157,3 +162,17 @@ def filter_bench(kind: str, H: int, W: int, iters: int = 20, device: int = 0):
     ms = C.c_float(0)
     check(load().vr_filter_bench(device, FILTER_KINDS[kind], H, W, iters, C.byref(ms)))
     return float(ms.value), FILTER_BYTES_PER_PX[kind] * H * W / (ms.value * 1e-3) / 1e9
+
+
+def pinned_array(shape, dtype=np.uint8):
+    """numpy array over page-locked host memory (freed when the array's base buffer is garbage collected)."""
+    lib = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.vr_host_alloc(n)
+    if not p:
+        raise VrError("vr_host_alloc failed")
+    buf = (C.c_uint8 * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.vr_host_free, C.c_void_p(p))
+    return arr

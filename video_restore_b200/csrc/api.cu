@@ -85,6 +85,11 @@ struct vr_handle {
     int prev_h = 0, prev_w = 0;
     DevBuf clahe_hist, clahe_lut;
     BlendState blend;
+    // pipelined host path (vr_submit / vr_wait): two slots
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    DevBuf pipe_in[2], pipe_out[2];
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int64_t submitted = 0;
     cudaEvent_t ev_total[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_net;
     size_t ev_used = 0;
@@ -590,6 +595,16 @@ void vr_destroy(vr_handle* h) {
     for (DevBuf* b : bufs) release(*b);
     for (auto& b : h->tile_out) release(b);
     free_blend_state(h->blend);
+    for (int i = 0; i < 2; ++i) {
+        release(h->pipe_in[i]);
+        release(h->pipe_out[i]);
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    if (h->dev.dep_buf) cudaFree(h->dev.dep_buf);
     for (auto e : h->ev_net) cudaEventDestroy(e);
     if (h->ev_total[0]) cudaEventDestroy(h->ev_total[0]);
     if (h->ev_total[1]) cudaEventDestroy(h->ev_total[1]);
@@ -722,6 +737,64 @@ int vr_restore(vr_handle* h, const uint8_t* bgr, int32_t H, int32_t W, int64_t s
                                     cudaMemcpyDeviceToHost, h->dev.stream),
                   h->dev.err);
     return finish_timing(h);
+}
+
+int vr_submit(vr_handle* h, const uint8_t* bgr, int32_t H, int32_t W, int64_t stride, uint8_t* out, int64_t out_stride,
+              const vr_frame_opts* opts, int64_t* ticket) {
+    if (!h) return VR_E_INVALID;
+    if (!bgr || !out || H <= 0 || W <= 0 || !ticket) return fail(h, VR_E_INVALID, "vr_submit: bad arguments");
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    if (!h->s_in) {
+        VR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking), h->dev.err);
+        VR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking), h->dev.err);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
+        }
+    }
+    const int slot = static_cast<int>(h->submitted & 1);
+    if (h->submitted >= 2) VR_CUDA_CHECK(cudaEventSynchronize(h->ev_out[slot]), h->dev.err);  // slot's previous frame left
+    const int s = h->cfg.scale;
+    const size_t in_row = static_cast<size_t>(W) * 3, out_row = static_cast<size_t>(W) * s * 3;
+    if (h->pipe_in[slot].bytes < in_row * H || h->pipe_out[slot].bytes < out_row * H * s) {
+        VR_CUDA_CHECK(cudaDeviceSynchronize(), h->dev.err);  // growing a slot: nothing may still use the old one
+        VR_TRY(ensure(h, h->pipe_in[slot], in_row * H));
+        VR_TRY(ensure(h, h->pipe_out[slot], out_row * H * s));
+    }
+    VR_CUDA_CHECK(cudaMemcpy2DAsync(h->pipe_in[slot].p, in_row, bgr, stride, in_row, H, cudaMemcpyHostToDevice, h->s_in),
+                  h->dev.err);
+    VR_CUDA_CHECK(cudaEventRecord(h->ev_in[slot], h->s_in), h->dev.err);
+    VR_CUDA_CHECK(cudaStreamWaitEvent(h->dev.stream, h->ev_in[slot], 0), h->dev.err);
+    VR_TRY(restore_enqueue(h, static_cast<const uint8_t*>(h->pipe_in[slot].p), H, W, in_row,
+                           static_cast<uint8_t*>(h->pipe_out[slot].p), out_row, opts));
+    VR_CUDA_CHECK(cudaEventRecord(h->ev_comp[slot], h->dev.stream), h->dev.err);
+    VR_CUDA_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0), h->dev.err);
+    VR_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, h->pipe_out[slot].p, out_row, out_row, static_cast<size_t>(H) * s,
+                                    cudaMemcpyDeviceToHost, h->s_out),
+                  h->dev.err);
+    VR_CUDA_CHECK(cudaEventRecord(h->ev_out[slot], h->s_out), h->dev.err);
+    *ticket = h->submitted++;
+    return VR_OK;
+}
+
+int vr_wait(vr_handle* h, int64_t ticket) {
+    if (!h) return VR_E_INVALID;
+    if (ticket < 0 || ticket >= h->submitted) return fail(h, VR_E_INVALID, "vr_wait: unknown ticket");
+    if (ticket + 2 < h->submitted) return VR_OK;  // its slot has been reused: that submit already waited for it
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    VR_CUDA_CHECK(cudaEventSynchronize(h->ev_out[ticket & 1]), h->dev.err);
+    return VR_OK;
+}
+
+void* vr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void vr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int vr_temporal_reset(vr_handle* h) {

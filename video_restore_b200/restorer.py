@@ -100,6 +100,45 @@ class FrameRestorer:
         _lib.check(rc, self._h)
         return out
 
+    def process_stream(self, frames, opts: FrameOpts | None = None):
+        """Generator over restored frames, in order, with H2D / compute / D2H of neighbouring frames overlapped
+        (vr_submit / vr_wait, two frames in flight). `frames` is any iterable of uint8 HxWx3 BGR arrays. Each yielded
+        array is a view of a pinned buffer that is overwritten three frames later: copy it to keep it longer."""
+        o = (opts or FrameOpts()).to_c()
+        n_slots = 3
+        ring_in, ring_out = getattr(self, "_rings", ([], []))  # pinned rings are kept across calls (slow to allocate)
+        i = 0
+        pending = []  # (ticket, out_array)
+        for frame in frames:
+            if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+                raise ValueError("frame must be uint8 HxWx3 BGR")
+            H, W, _ = frame.shape
+            s = self.scale
+            if not ring_in or ring_in[0].shape != frame.shape:
+                while pending:
+                    t, out = pending.pop(0)
+                    _lib.check(self._lib.vr_wait(self._h, t), self._h)
+                    yield out
+                ring_in = [_lib.pinned_array((H, W, 3)) for _ in range(n_slots)]
+                ring_out = [_lib.pinned_array((H * s, W * s, 3)) for _ in range(n_slots)]
+                self._rings = (ring_in, ring_out)
+            slot = i % n_slots
+            if len(pending) >= 2:  # keep two in flight: the slot about to be reused has been handed out already
+                t, out = pending.pop(0)
+                _lib.check(self._lib.vr_wait(self._h, t), self._h)
+                yield out
+            np.copyto(ring_in[slot], frame)
+            ticket = C.c_int64(0)
+            _lib.check(self._lib.vr_submit(self._h, ring_in[slot].ctypes.data_as(C.c_void_p), H, W,
+                                           ring_in[slot].strides[0], ring_out[slot].ctypes.data_as(C.c_void_p),
+                                           ring_out[slot].strides[0], C.byref(o), C.byref(ticket)), self._h)
+            pending.append((int(ticket.value), ring_out[slot]))
+            i += 1
+        while pending:
+            t, out = pending.pop(0)
+            _lib.check(self._lib.vr_wait(self._h, t), self._h)
+            yield out
+
     def process_frame_device(self, d_in: int, H: int, W: int, d_out: int, opts: FrameOpts | None = None,
                              sync: bool = True) -> None:
         """Device-resident frames (raw pointers on this restorer's GPU), dense rows."""
