@@ -334,3 +334,27 @@ def test_process_stream_equals_per_frame_calls(gpu_lib):
     for a, b in zip(got, ref):
         assert np.array_equal(a, b)
     gpu.close()
+
+
+def test_pth_checkpoint_loading(gpu_lib, tmp_path):
+    """a .pth with `params_ema` (upstream key names) loads through the RealESRGANer-shaped constructor."""
+    import torch
+
+    from video_restore_b200.restorer import RealESRGANer
+
+    name = "RealESRGAN_x4_v3"
+    sd = random_state_dict(name, seed=0)
+    path = tmp_path / "realesr-general-x4v3.pth"
+    torch.save({"params_ema": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, path)
+    f = synth_frame(40, 56, seed=4)
+    a, _ = RealESRGANer(scale=4, model_path=str(path), model=name, tile=32, tile_pad=10, pre_pad=0, half=True).enhance(f, 4)
+    b, _ = RealESRGANer(scale=4, model=name, tile=32, tile_pad=10, pre_pad=0, half=True, state_dict=sd).enhance(f, 4)
+    assert np.array_equal(a, b)
+
+
+def test_cli_synthetic_run(gpu_lib, capsys):
+    from video_restore_b200.cli import main
+
+    assert main(["in.mp4", "out.mp4", "--model", "RealESRGAN_x4_v3", "--quality", "fast", "--enhanced",
+                 "--synthetic", "2"]) == 0
+    assert "processed 2 frames" in capsys.readouterr().out

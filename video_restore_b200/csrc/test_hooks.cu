@@ -79,7 +79,13 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     __half *dx = nullptr, *dy = nullptr, *dr1 = nullptr, *dr2 = nullptr;
     const size_t out_elems = ps4 ? px * 16 * 4 : px * out_c;
     VR_CUDA_CHECK(cudaMalloc(&dx, hx.size() * sizeof(__half)), dev.err);
-    VR_CUDA_CHECK(cudaMalloc(&dy, out_elems * sizeof(__half)), dev.err);
+    // guard bands of 0xA5 before and after the output: the epilogue's store masks are checked, not trusted
+    // (compute-sanitizer is not available on this pool)
+    constexpr size_t kGuard = 8192;
+    uint8_t* dy_raw = nullptr;
+    VR_CUDA_CHECK(cudaMalloc(&dy_raw, out_elems * sizeof(__half) + 2 * kGuard), dev.err);
+    VR_CUDA_CHECK(cudaMemset(dy_raw, 0xA5, out_elems * sizeof(__half) + 2 * kGuard), dev.err);
+    dy = reinterpret_cast<__half*>(dy_raw + kGuard);
     VR_CUDA_CHECK(cudaMemset(dy, 0, out_elems * sizeof(__half)), dev.err);
     VR_CUDA_CHECK(cudaMemcpy(dx, hx.data(), hx.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
     if (t->res1) {
@@ -140,6 +146,15 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
         t->ms = ms;
         std::vector<__half> hy(out_elems);
         cudaMemcpy(hy.data(), dy, out_elems * sizeof(__half), cudaMemcpyDeviceToHost);
+        std::vector<uint8_t> g0(kGuard), g1(kGuard);
+        cudaMemcpy(g0.data(), dy_raw, kGuard, cudaMemcpyDeviceToHost);
+        cudaMemcpy(g1.data(), dy_raw + kGuard + out_elems * sizeof(__half), kGuard, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < kGuard; ++i)
+            if (g0[i] != 0xA5 || g1[i] != 0xA5) {
+                set_error(dev.err, "conv kernel wrote outside its output tensor (guard band damaged)");
+                rc = VR_E_CUDA;
+                break;
+            }
         if (ps4) {
             // [4H][4W][4] fp16 -> y[4H][4W][3] fp32
             for (size_t i = 0; i < px * 16; ++i)
@@ -152,7 +167,7 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(dx);
-    cudaFree(dy);
+    cudaFree(dy_raw);
     if (dr1) cudaFree(dr1);
     if (dr2) cudaFree(dr2);
     free_conv_weights(&w);
