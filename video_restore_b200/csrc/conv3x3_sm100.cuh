@@ -104,8 +104,9 @@ struct ConvTraits {
     static constexpr int kBStage = round_up_c(kBBytes, 1024);
     static constexpr int kStageBytes = kAStage + kBStage;
     static constexpr int kStatic = 2048;  // static __shared__: barriers, tmem slot, per-layer bias / activation tables
-    // per-warp epilogue staging (NHWC outputs only): 32 pixels x (N fp16 + 16 B pad) for the coalescing transpose
-    static constexpr int kStgPitch = N * 2 + 16;
+    // per-warp epilogue staging (NHWC outputs only): 32 pixels x N fp16 for the coalescing transpose; 16 B unit U of
+    // pixel p lives at unit U ^ swz(p) (conflict-free for the per-pixel writes and the per-row reads, no padding)
+    static constexpr int kStgPitch = N * 2;
     static constexpr int kStgWarp = (N % 32 == 0) ? 32 * kStgPitch : 0;
     static constexpr int kStgBytes = kEpiWarps * kStgWarp;
     static constexpr int kBudget = 227 * 1024 - 1024 - kStatic - kStgBytes;
@@ -408,7 +409,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         // activation mode for bias_act: 0 identity, 1 max-form LeakyReLU, 2 general
         const int amode = a.act == ACT_NONE ? 0 : ((a.act == ACT_LRELU && a.slope >= 0.f && a.slope <= 1.f) ? 1 : 2);
         const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
-        uint8_t* stg = stage0 + nstages * a.stage_bytes + warp * T::kStgWarp;
+        const uint32_t stg_s = ptx::smem_u32(stage0 + nstages * a.stage_bytes + warp * T::kStgWarp);
         int it = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -521,9 +522,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
                             }
                             // stage this pixel's 32 channels (64 B) in the per-warp transpose buffer
-                            uint4* sp = reinterpret_cast<uint4*>(stg + lane * T::kStgPitch + g * 64);
+                            constexpr int kU = N / 8;  // 16 B units per pixel
+                            const int swz_w = kU == 8 ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) sp[u] = pack8(v + u * 8);
+                            for (int u = 0; u < 4; ++u)
+                                ptx::sts128(stg_s + lane * T::kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
                         }
                         __syncwarp();
                         // coalesced write-out: consecutive lanes write consecutive 16 B units of the same pixel
@@ -537,7 +540,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                             const int idx = i * 32 + lane;
                             const int px = idx / kUnits, un = idx % kUnits;
                             if (x_base + px < a.W) {
-                                const uint4 val = *reinterpret_cast<const uint4*>(stg + px * T::kStgPitch + un * 16);
+                                const int swz_r = kUnits == 8 ? (px & 7) : ((px >> 1) & 3);
+                                const uint4 val = ptx::lds128(stg_s + px * T::kStgPitch + ((un ^ swz_r) << 4));
                                 *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
                             }
                         }
