@@ -99,6 +99,37 @@ def main():
         case("cin12", 12, 140, 12, 64)
         case("rgb", 12, 140, 64, 3)
         case("ps4", 12, 140, 64, 48)
+    elif group == "roll":
+        R = 128  # FLAG_FORCE_ROLL
+        case("r-basic", 8, 128, 32, 32, flags=R)
+        case("r-2chunk", 8, 128, 64, 32, flags=R)
+        case("r-tall", 75, 128, 64, 32, flags=R)          # ring wraps (16 blocks) several times
+        case("r-tall64", 75, 200, 64, 64, flags=R)        # ring of 8
+        case("r-multi", 37, 300, 64, 32, flags=R)
+        case("r-cin160", 40, 256, 160, 32, flags=R)
+        case("r-split", 41, 200, 192, 64, flags=R)        # two resident 32-channel halves
+        case("r-split-res2", 23, 140, 192, 64, res=2, flags=R)
+        case("r-lrelu", 12, 140, 64, 32, act=1, flags=R)
+        case("r-prelu", 12, 140, 64, 64, prelu=True, flags=R)
+        case("r-small", 5, 17, 64, 64, flags=R)
+        case("r-1row", 1, 33, 64, 32, flags=R)
+        case("r-2row", 2, 130, 96, 32, flags=R)
+        case("r-cin3", 12, 140, 3, 64, flags=R)
+        case("r-big", 720, 1280, 64, 32, flags=R)         # 140 items, bands of 52 rows
+        case("r-big-split", 300, 1280, 192, 64, res=2, flags=R)
+    elif group == "rbench":
+        H, W = 720, 1280
+        for cin, cout in [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64), (64, 64)]:
+            for label, rows, fl in (("K1", 4, 0), ("K2", 0, 128), ("K2-skip-epi", 0, 128 + 8), ("K2-skip-mma", 0, 128 + 4),
+                                    ("K2-skip-tma", 0, 128 + 2)):
+                try:
+                    ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, flags=fl, iters=20)
+                    cyc = _lib.last_conv_cycles()
+                    print(f"[rbench] {cin}->{cout} {label:>12}: {ms*1e3:8.1f} us  {2.0*H*W*cin*cout*9/ms/1e9:7.1f} TFLOP/s  "
+                          f"{cyc} cyc/CTA -> {cyc / (ms * 1e3):.0f} MHz", flush=True)
+                except Exception as e:  # noqa: BLE001
+                    print(f"[rbench] {cin}->{cout} {label}: ERROR {e}", flush=True)
+                    return
     elif group == "one":
         cin, cout = int(sys.argv[2]), int(sys.argv[3])
         fl = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 0

@@ -30,7 +30,11 @@ enum ConvAct { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2 };
 enum ConvOut { OUT_NHWC = 0, OUT_RGB4 = 1, OUT_PS4 = 2 };
 // debug ablation flags (ConvArgs::flags): measurement only
 constexpr int kMaxLayers = 4;
-enum ConvFlags { FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8, FLAG_SKIP_B = 16, FLAG_SKIP_A = 32 };
+enum ConvFlags {
+    FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8, FLAG_SKIP_B = 16, FLAG_SKIP_A = 32,
+    FLAG_FORCE_TILE = 64,  // kernel selection (tests): always the tiled kernel K1 ...
+    FLAG_FORCE_ROLL = 128  // ... or fail unless the rolling-row kernel K2 takes the layer
+};
 
 struct ConvArgs {
     int W, H;              // conv input == output extent
@@ -79,6 +83,9 @@ struct ConvArgs {
     int* dep;         // [nlayers][tiles_y], zero on entry
     int* dep_zero;    // the other launch parity's region: zeroed by this launch for the next multi-layer launch
     int dep_zero_n;
+    // Rolling-row kernel K2 (conv3x3_roll_sm100.cuh): work item = (band of `band` output rows, 128-pixel strip, channel half)
+    int band, nbands;
+    int nsplit;  // 1, or 2: the layer's 2N output channels are computed as two independent N-channel halves
     long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 
@@ -157,6 +164,84 @@ __device__ __forceinline__ void bias_act(float* v, const float* s_bias, const fl
             v[j] = fmaxf(t, 0.f) + s_neg[c0 + j] * fminf(t, 0.f);
         }
     }
+}
+
+// One output row x 32 pixels (this warp's TMEM lane quarter) of an NHWC layer:
+// tcgen05.ld -> +bias -> activation -> *s1 + res1 -> *s2 + res2 (fp32) -> fp16 -> per-warp swizzled staging transpose ->
+// coalesced 16 B stores (consecutive lanes write consecutive units of one pixel). `t_addr` = TMEM address of the row's
+// first accumulator column in this warp's lane quarter; `coff_add` shifts the output / residual channel slices (the
+// second half of a layer computed as two N-channel halves); s_bias / s_neg are already offset to channel 0 of the slice.
+// Residual rows are fetched before the TMEM loads: one global-load latency per row instead of one per channel group.
+template <int N>
+__device__ __forceinline__ void epi_row_nhwc(const ConvArgs& a, uint32_t t_addr, uint32_t stg_s, int lane, int x_base, int y,
+                                             bool gap, int out_coff, int coff_add, const float* s_bias, const float* s_neg,
+                                             int amode) {
+    constexpr int kVec = N / 8;  // 16 B units per pixel
+    constexpr int kStgPitch = N * 2;
+    const int x = x_base + lane;
+    const bool inb = x < a.W;
+    const size_t p = static_cast<size_t>(y) * a.W + x;
+    const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
+    uint4 q1[kVec], q2[kVec];
+    if (inb && has1) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff + coff_add);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
+    }
+    if (inb && has2) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff + coff_add);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
+    }
+#pragma unroll
+    for (int g = 0; g < N / 32; ++g) {
+        float v[32];
+        ptx::tmem_ld32(t_addr + g * 32, v);
+        if (inb) {
+            const int c0 = g * 32;
+            bias_act<32>(v, s_bias, s_neg, c0, amode);
+            if (has1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(q1[g * 4 + u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
+                }
+            }
+            if (has2) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(q2[g * 4 + u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
+                }
+            }
+        }
+        if (gap) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        // stage this pixel's 32 channels (64 B): unit U of pixel p lives at U ^ swz(p) (conflict-free both ways)
+        const int swz_w = kVec == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
+    }
+    __syncwarp();
+    __half* orow = a.out + out_coff + coff_add +
+                   (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) * a.out_cstride;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int idx = i * 32 + lane;
+        const int px = idx / kVec, un = idx % kVec;
+        if (x_base + px < a.W) {
+            const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
+            const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
+            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
+        }
+    }
+    __syncwarp();
 }
 
 // DYS / DXS select the taps that are present: 0 = all three, 1 = {0, 1}, 2 = {1, 2} (the 2x2 sub-kernels of the four
@@ -408,7 +493,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         const int rgrp = warp >> 2;    // rows rgrp, rgrp + 2, ...
         // activation mode for bias_act: 0 identity, 1 max-form LeakyReLU, 2 general
         const int amode = a.act == ACT_NONE ? 0 : ((a.act == ACT_LRELU && a.slope >= 0.f && a.slope <= 1.f) ? 1 : 2);
-        const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
         const uint32_t stg_s = ptx::smem_u32(stage0 + nstages * a.stage_bytes + warp * T::kStgWarp);
         int it = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
@@ -477,74 +561,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                     }
                 } else {
                     if constexpr (N % 32 == 0) {
-                        // all residual loads of the row are issued before the TMEM loads: one global-load latency
-                        // per row instead of one per channel group
-                        constexpr int kVec = N / 8;
-                        uint4 q1[kVec], q2[kVec];
-                        if (inb && has1) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff);
-#pragma unroll
-                            for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
-                        }
-                        if (inb && has2) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff);
-#pragma unroll
-                            for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
-                        }
-#pragma unroll
-                        for (int g = 0; g < N / 32; ++g) {
-                            float v[32];
-                            ptx::tmem_ld32(t_row0 + r * N + g * 32, v);
-                            if (inb) {
-                                const int c0 = g * 32;
-                                bias_act<32>(v, s_bias, s_neg, c0, amode);
-                                if (has1) {
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        float f[8];
-                                        unpack8(q1[g * 4 + u], f);
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
-                                    }
-                                }
-                                if (has2) {
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        float f[8];
-                                        unpack8(q2[g * 4 + u], f);
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
-                                    }
-                                }
-                            }
-                            if (gap) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                            }
-                            // stage this pixel's 32 channels (64 B) in the per-warp transpose buffer
-                            constexpr int kU = N / 8;  // 16 B units per pixel
-                            const int swz_w = kU == 8 ? (lane & 7) : ((lane >> 1) & 3);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                ptx::sts128(stg_s + lane * T::kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
-                        }
-                        __syncwarp();
-                        // coalesced write-out: consecutive lanes write consecutive 16 B units of the same pixel
-                        constexpr int kUnits = N / 8;  // 16 B units per pixel
-                        const int x_base = tx * 128 + quarter * 32;
-                        __half* orow = a.out + out_coff +
-                                       (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) *
-                                           a.out_cstride;
-#pragma unroll
-                        for (int i = 0; i < kUnits; ++i) {
-                            const int idx = i * 32 + lane;
-                            const int px = idx / kUnits, un = idx % kUnits;
-                            if (x_base + px < a.W) {
-                                const int swz_r = kUnits == 8 ? (px & 7) : ((px >> 1) & 3);
-                                const uint4 val = ptx::lds128(stg_s + px * T::kStgPitch + ((un ^ swz_r) << 4));
-                                *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
-                            }
-                        }
+                        epi_row_nhwc<N>(a, t_row0 + r * N, stg_s, lane, tx * 128 + quarter * 32, y, gap, out_coff, 0, s_bias, s_neg,
+                                        amode);
                         __syncwarp();
                     }
                 }

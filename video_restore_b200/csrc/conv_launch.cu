@@ -1,6 +1,6 @@
-// Host side of K1: weight repacking into the swizzled shared-memory image, TMA tensor-map construction,
+// Host side of K1 / K2: weight repacking into the swizzled shared-memory image, TMA tensor-map construction,
 // kernel selection and launch. See conv3x3_sm100.cuh for the kernel.
-#include "conv3x3_sm100.cuh"
+#include "conv3x3_roll_sm100.cuh"
 #include "vr_common.h"
 
 #include <cstdlib>
@@ -53,7 +53,7 @@ static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 1};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(W) * cstride * 2,
                              static_cast<cuuint64_t>(H) * W * cstride * 2};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 130, static_cast<cuuint32_t>(rows + 2), 1};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 130, static_cast<cuuint32_t>(rows + 2), 1};  // rows = -1: one line (K2)
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(ptr), dims, strides, box, estr,
@@ -119,6 +119,24 @@ int pack_conv_weights(Device& dev, const float* w, const float* bias, const floa
     VR_CUDA_CHECK(cudaMalloc(&cw.wpack, elems * sizeof(__half)), dev.err);
     VR_CUDA_CHECK(cudaMemcpyAsync(cw.wpack, img.data(), elems * sizeof(__half), cudaMemcpyHostToDevice, dev.stream),
                   dev.err);
+    if (cout == 64 && kc == 32) {
+        // the same layer as two independent 32-channel halves [half][chunk][tap][32][kc] for the rolling kernel, whose
+        // resident-weight budget a 64-channel layer with more than four chunks exceeds
+        std::vector<__half> simg(elems, __float2half(0.f));
+        const size_t half_elems = static_cast<size_t>(cw.nchunks) * 9 * 32 * kc;
+        for (int n = 0; n < 64; ++n)
+            for (int c = 0; c < cw.nchunks; ++c)
+                for (int t = 0; t < 9; ++t) {
+                    const size_t src = ((static_cast<size_t>(c) * 9 + t) * 64 + n) * kc;  // rows are already tap-ordered
+                    const size_t dst = (n >> 5) * half_elems + ((static_cast<size_t>(c) * 9 + t) * 32 + (n & 31)) * kc;
+                    // the swizzle depends on (n >> 1) & 3 only, identical for n and n & 31
+                    std::memcpy(&simg[dst], &img[src], kc * sizeof(__half));
+                }
+        VR_CUDA_CHECK(cudaMalloc(&cw.wsplit, elems * sizeof(__half)), dev.err);
+        VR_CUDA_CHECK(cudaMemcpyAsync(cw.wsplit, simg.data(), elems * sizeof(__half), cudaMemcpyHostToDevice, dev.stream),
+                      dev.err);
+        VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);
+    }
     std::vector<float> b(cout, 0.f);
     if (bias) std::memcpy(b.data(), bias, cout * sizeof(float));
     VR_CUDA_CHECK(cudaMalloc(&cw.bias, cout * sizeof(float)), dev.err);
@@ -136,6 +154,7 @@ int pack_conv_weights(Device& dev, const float* w, const float* bias, const floa
 
 void free_conv_weights(ConvWeights* w) {
     if (w->wpack) cudaFree(w->wpack);
+    if (w->wsplit) cudaFree(w->wsplit);
     if (w->bias) cudaFree(w->bias);
     if (w->prelu) cudaFree(w->prelu);
     *w = ConvWeights();
@@ -179,6 +198,63 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     cfg.stream = dev.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: prologue overlaps the previous kernel
+    attr[0].val.programmaticStreamSerializationAllowed = dev.use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
+    dev.launches++;
+    return 0;
+}
+
+// K2 work split: bands of output rows x 128-pixel strips (x channel halves). One wave of equal items is ideal; the cost
+// model is waves x (band + 2 halo rows + ~2 rows of pipeline fill), minimised over the band count.
+static void choose_bands(int units, int rows, int sms, int* band, int* nbands) {
+    long best_cost = -1;
+    for (int nb = 1; nb <= rows; ++nb) {
+        const int bd = (rows + nb - 1) / nb;
+        if (bd < 4 && nb > 1) break;
+        const int real_nb = (rows + bd - 1) / bd;
+        const long items = static_cast<long>(units) * real_nb;
+        const long waves = (items + sms - 1) / sms;
+        const long cost = waves * (bd + 4);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            *band = bd;
+            *nbands = real_nb;
+        }
+    }
+}
+
+// returns 1 when the layer is not a K2 shape (caller falls back to K1), 0 on launch, < 0 on error
+template <int N>
+static int launch_roll(Device& dev, const CUtensorMap& tm, ConvArgs a, const ConvWeights& w) {
+    using T = RollTraits<N>;
+    const int w_bytes = w.nchunks * T::kBStage;
+    int nslots = (T::kBudget - w_bytes) / T::kASlot;
+    if (nslots < T::kMinSlots) return 1;
+    if (nslots > kRollMaxSlots) nslots = kRollMaxSlots;
+    auto kern = conv3x3_roll_kernel<N>;
+    static bool attr_done[64] = {};
+    if (!attr_done[dev.ordinal & 63]) {
+        VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kBudget + T::kStgBytes + 1024),
+                      dev.err);
+        attr_done[dev.ordinal & 63] = true;
+    }
+    a.nsplit = w.npad / N;
+    a.wpack = a.nsplit == 2 ? w.wsplit : w.wpack;
+    a.nstages = nslots;
+    a.tiles_x = (a.W + 127) / 128;
+    choose_bands(a.tiles_x * a.nsplit, a.y_end - a.y_begin, dev.sm_count, &a.band, &a.nbands);
+    const int items = a.tiles_x * a.nbands * a.nsplit;
+    int grid = items < dev.sm_count ? items : dev.sm_count;
+    grid -= grid % a.nsplit;  // a CTA keeps one channel half resident
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = w_bytes + nslots * T::kASlot + T::kStgBytes + 1024;
+    cfg.stream = dev.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = dev.use_pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
@@ -275,6 +351,22 @@ int run_conv(Device& dev, const ConvCall& c) {
     }
     if (c.out_mode == OUT_PS4 && w.npad != 48) {
         set_error(dev.err, "run_conv: pixel-shuffle output needs cout == 48");
+        return -1;
+    }
+    const bool roll_shape = c.out_mode == OUT_NHWC && c.nlayers == 1 && !c.dys && !c.dxs && c.rows == 0 && w.kc == 32 &&
+                            (w.cout == 32 || w.cout == 64);
+    if (roll_shape && !(c.flags & FLAG_FORCE_TILE) && (dev.rolling || (c.flags & FLAG_FORCE_ROLL))) {
+        CUtensorMap tm1;
+        rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, -1, w.kc, &tm1);
+        if (rc) return rc;
+        rc = 1;
+        if (w.cout == 64) rc = launch_roll<64>(dev, tm1, a, w);            // whole layer resident
+        if (rc == 1 && w.wpack) rc = w.cout == 64 ? (w.wsplit ? launch_roll<32>(dev, tm1, a, w) : 1)  // two resident halves
+                                                  : launch_roll<32>(dev, tm1, a, w);
+        if (rc <= 0) return rc;
+    }
+    if (c.flags & FLAG_FORCE_ROLL) {
+        set_error(dev.err, "run_conv: the rolling-row kernel does not take this layer");
         return -1;
     }
     if (c.dys || c.dxs) {

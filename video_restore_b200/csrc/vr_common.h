@@ -31,6 +31,7 @@ struct ConvWeights {
     int kc = 32;      // channels per pipeline stage (16 or 32)
     int nchunks = 0;  // ceil(cin / kc)
     __half* wpack = nullptr;  // device, [nchunks][dx][dy=2,1,0][npad][kc] swizzled
+    __half* wsplit = nullptr; // device, cout == 64 only: the layer as two 32-channel halves [half][nchunks][tap][32][kc]
     float* bias = nullptr;    // device [cout]
     float* prelu = nullptr;   // device [cout] or null
 };
@@ -87,6 +88,7 @@ struct Device {
     bool multi_layer = false;
     bool fold_upsample = true;     // VR_FOLD_UP=0: materialise nearest x2 and run conv_up1/2 as plain 3x3 convs
     bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
+    bool rolling = true;  // VR_ROLL=0: never use the rolling-row kernel K2 (NHWC body layers run on the tiled kernel K1)
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc)
     std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
