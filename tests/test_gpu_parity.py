@@ -21,7 +21,10 @@ CONV_ATOL, CONV_RTOL = 2e-2, 4e-3   # single conv, fp16 storage vs fp32 referenc
 # ----------------------------------------------------------------------------------------------------------
 # K1: single convolution against torch.nn.functional.conv2d (fp32, CPU)
 # ----------------------------------------------------------------------------------------------------------
-def _conv_case(gpu_lib, H, W, cin, cout, act=0, prelu=False, res=0, rows=0, seed=0):
+FORCE_TILE, FORCE_ROLL = 64, 128   # ConvFlags: kernel selection in the conv hook (K1 tiled / K2 rolling-row)
+
+
+def _conv_case(gpu_lib, H, W, cin, cout, act=0, prelu=False, res=0, rows=0, seed=0, flags=0):
     import torch
     import torch.nn.functional as F
 
@@ -48,7 +51,8 @@ def _conv_case(gpu_lib, H, W, cin, cout, act=0, prelu=False, res=0, rows=0, seed
     if cout == 48:
         ref = ref.reshape(H, W, 3, 4, 4).transpose(0, 3, 1, 4, 2).reshape(4 * H, 4 * W, 3)
         ref = ref + np.repeat(np.repeat(x[:, :, :3], 4, axis=0), 4, axis=1)
-    y, _ = _lib.conv3x3(x, w, b, act=2 if prelu else act, prelu=pr, res1=r1, s1=0.2, res2=r2, s2=0.2, rows=rows)
+    y, _ = _lib.conv3x3(x, w, b, act=2 if prelu else act, prelu=pr, res1=r1, s1=0.2, res2=r2, s2=0.2, rows=rows,
+                        flags=flags)
     err = np.abs(y - ref)
     assert (err <= CONV_ATOL + CONV_RTOL * np.abs(ref)).all(), f"max err {err.max():.3e}"
 
@@ -58,13 +62,38 @@ def _conv_case(gpu_lib, H, W, cin, cout, act=0, prelu=False, res=0, rows=0, seed
                                           (12, 140, 3, 64), (12, 140, 12, 64), (12, 140, 64, 3), (12, 140, 64, 48),
                                           (3, 129, 128, 32), (131, 130, 64, 32)])
 def test_conv_shapes(gpu_lib, H, W, cin, cout):
-    _conv_case(gpu_lib, H, W, cin, cout)
+    _conv_case(gpu_lib, H, W, cin, cout, flags=FORCE_TILE)      # K1 on every shape
+    _conv_case(gpu_lib, H, W, cin, cout)                        # default dispatch (K2 where it is enabled)
+
+
+# K2 (rolling-row kernel): bands, TMEM ring wrap (16 blocks at 32 channels, 8 at 64), band edges of 1 / 2 / 3 rows, the
+# 192 -> 64 layer as two resident halves, partial last strip, several strips x bands > SM count
+@pytest.mark.parametrize("H,W,cin,cout", [(8, 128, 32, 32), (75, 128, 64, 32), (75, 200, 64, 64), (37, 300, 64, 32),
+                                          (40, 256, 160, 32), (41, 200, 192, 64), (5, 17, 64, 64), (1, 33, 64, 32),
+                                          (2, 130, 96, 32), (3, 129, 128, 32), (12, 140, 3, 64), (12, 140, 12, 64),
+                                          (131, 130, 64, 32), (300, 1280, 128, 32)])
+def test_conv_rolling_shapes(gpu_lib, H, W, cin, cout):
+    _conv_case(gpu_lib, H, W, cin, cout, flags=FORCE_ROLL)
+
+
+@pytest.mark.parametrize("kw", [dict(act=1, cout=32), dict(prelu=True, cout=64), dict(prelu=True, cout=32), dict(res=1, cout=64),
+                                dict(res=2, cout=64), dict(res=2, cout=32, act=1)])
+def test_conv_rolling_epilogues(gpu_lib, kw):
+    kw = dict(kw)
+    cout = kw.pop("cout")
+    _conv_case(gpu_lib, 23, 140, 192 if cout == 64 and "res" in kw else 64, cout, flags=FORCE_ROLL, **kw)
+
+
+def test_conv_rolling_rejects_other_layers(gpu_lib):
+    from video_restore_b200._lib import VrError
+    with pytest.raises(VrError):
+        _conv_case(gpu_lib, 12, 140, 64, 3, flags=FORCE_ROLL)   # RGB output stays on K1
 
 
 @pytest.mark.parametrize("kw", [dict(act=1), dict(prelu=True), dict(res=1), dict(res=2), dict(act=1, rows=8)])
 def test_conv_epilogues(gpu_lib, kw):
     cout = 32 if kw.get("rows") == 8 or kw.get("act") == 1 else 64
-    _conv_case(gpu_lib, 12, 140, 64 if cout == 32 else 192, cout, **kw)
+    _conv_case(gpu_lib, 12, 140, 64 if cout == 32 else 192, cout, flags=FORCE_TILE, **kw)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -274,8 +303,10 @@ def test_full_size_480p_srvgg_crop_property(gpu_lib):
 
 def test_full_size_720p_x4plus_runs_and_is_tile_consistent(gpu_lib):
     """BASELINE configs[3] size. The oracle needs ~1 min/frame here, so parity at this size is checked through
-    properties: determinism, and crop-merge tiling vs single tile differing by <= 1 LSB on < 0.5 % of pixels
-    (tile borders only matter through zero padding 10+ px away)."""
+    properties: determinism, and crop-merge tiling vs single tile differing by <= 1 LSB on < 2 % of pixels
+    (tile borders only matter through zero padding 10+ px away; K2 sums an output row's taps in an
+    order that depends on the row's parity inside its band, so identical tile interiors can round differently in fp16:
+    0.5 % with K1 only, 1.2 % with K2 on the 32-channel layers)."""
     from video_restore_b200.restorer import FrameRestorer
 
     sd = random_state_dict("RealESRGAN_x4plus", seed=0)
@@ -288,7 +319,7 @@ def test_full_size_720p_x4plus_runs_and_is_tile_consistent(gpu_lib):
     b = tiled.process_frame(f)
     tiled.close()
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
-    assert a.shape == (2880, 5120, 3) and d.max() <= 1 and (d > 0).mean() < 5e-3
+    assert a.shape == (2880, 5120, 3) and d.max() <= 1 and (d > 0).mean() < 2e-2
     assert a.std() > 2.0
 
 
@@ -313,11 +344,20 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
             monkeypatch.delenv(k)
         return out, n
 
-    base, n_base = run({})
-    multi, n_multi = run({"VR_MULTI": "1"})
+    # K1 only (VR_ROLL=0): every scheduling variant is bit-identical
+    base, n_base = run({"VR_ROLL": "0"})
+    multi, n_multi = run({"VR_ROLL": "0", "VR_MULTI": "1"})
     assert np.array_equal(base, multi) and n_multi < n_base
-    assert np.array_equal(base, run({"VR_PDL": "0"})[0])
-    assert np.array_equal(base, run({"VR_WRES": "0"})[0])
+    assert np.array_equal(base, run({"VR_ROLL": "0", "VR_PDL": "0"})[0])
+    assert np.array_equal(base, run({"VR_ROLL": "0", "VR_WRES": "0"})[0])
+    # K2 on its layer classes: deterministic and independent of PDL; against K1 the fp32 summation order differs (bias is the
+    # accumulator's initial value, taps are summed row by row), so the 8-bit frames agree within one level
+    for mask in ("1", "7"):
+        roll = run({"VR_ROLL": mask})[0]
+        assert np.array_equal(roll, run({"VR_ROLL": mask})[0])
+        assert np.array_equal(roll, run({"VR_ROLL": mask, "VR_PDL": "0"})[0])
+        d = np.abs(roll.astype(np.int32) - base.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 2e-2
 
 
 def test_process_stream_equals_per_frame_calls(gpu_lib):

@@ -572,7 +572,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     h->dev.sm_count = p.multiProcessorCount;
     h->dev.err = &h->err;
     if (const char* e = std::getenv("VR_PDL")) h->dev.use_pdl = std::atoi(e) != 0;
-    if (const char* e = std::getenv("VR_ROLL")) h->dev.rolling = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_ROLL")) h->dev.rolling = std::atoi(e);
     if (const char* e = std::getenv("VR_WRES")) h->dev.weights_resident = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;

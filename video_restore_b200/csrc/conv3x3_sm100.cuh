@@ -33,7 +33,8 @@ constexpr int kMaxLayers = 4;
 enum ConvFlags {
     FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8, FLAG_SKIP_B = 16, FLAG_SKIP_A = 32,
     FLAG_FORCE_TILE = 64,  // kernel selection (tests): always the tiled kernel K1 ...
-    FLAG_FORCE_ROLL = 128  // ... or fail unless the rolling-row kernel K2 takes the layer
+    FLAG_FORCE_ROLL = 128,  // ... or fail unless the rolling-row kernel K2 takes the layer
+    FLAG_TRACE = 256        // K2: CTA 0's issuers record per-box timestamps into dbg_cycles[256..512) (bench hook prints them)
 };
 
 struct ConvArgs {
@@ -229,6 +230,113 @@ __device__ __forceinline__ void epi_row_nhwc(const ConvArgs& a, uint32_t t_addr,
         for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
     }
     __syncwarp();
+    __half* orow = a.out + out_coff + coff_add +
+                   (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) * a.out_cstride;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int idx = i * 32 + lane;
+        const int px = idx / kVec, un = idx % kVec;
+        if (x_base + px < a.W) {
+            const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
+            const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
+            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
+        }
+    }
+    __syncwarp();
+}
+
+// K2's variant of epi_row_nhwc. The accumulators already contain the bias (the ring block was initialised with it), all
+// TMEM loads of the row are issued before one wait, and the block is re-initialised and released (`release`) BEFORE the
+// arithmetic and the stores, so the MMAs of a later row can start while this row is still being written out.
+// amode: 0 identity, 1 LeakyReLU with the scalar a.slope in [0, 1], 2 per-channel s_neg table (PReLU).
+template <int N>
+__device__ __forceinline__ void epi_row_nhwc_folded(const ConvArgs& a, uint32_t t_addr, uint32_t stg_s, int lane, int x_base, int y,
+                                                    bool gap, int out_coff, int coff_add, const float* s_bias, const float* s_neg,
+                                                    int amode, uint64_t* release, long long* tr = nullptr, long long t_ref = 0) {
+    constexpr int kVec = N / 8;  // 16 B units per pixel
+    constexpr int kStgPitch = N * 2;
+    const int x = x_base + lane;
+    const bool inb = x < a.W;
+    const size_t p = static_cast<size_t>(y) * a.W + x;
+    const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
+    uint4 q1[kVec], q2[kVec];
+    if (inb && has1) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff + coff_add);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
+    }
+    if (inb && has2) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff + coff_add);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
+    }
+    uint32_t raw[N];
+#pragma unroll
+    for (int g = 0; g < N / 32; ++g) ptx::tmem_ld32_issue(t_addr + g * 32, raw + g * 32);
+#pragma unroll
+    for (int g = 0; g < N / 32; ++g) ptx::tmem_ld32_wait(raw + g * 32);
+    if (tr) tr[2] = clock64() - t_ref;
+    {
+        // re-initialise the block with the bias and hand it back
+#pragma unroll
+        for (int g = 0; g < N / 32; ++g) {
+            float bz[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(s_bias + g * 32 + j * 4);
+                bz[j * 4] = t.x; bz[j * 4 + 1] = t.y; bz[j * 4 + 2] = t.z; bz[j * 4 + 3] = t.w;
+            }
+            ptx::tmem_st32(t_addr + g * 32, bz);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(release);
+    }
+    if (tr) tr[3] = clock64() - t_ref;
+#pragma unroll
+    for (int g = 0; g < N / 32; ++g) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[g * 32 + j]);
+        if (inb) {
+            if (amode == 1) {
+                const float sl = a.slope;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * sl);
+            } else if (amode == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + s_neg[g * 32 + j] * fminf(v[j], 0.f);
+            }
+            if (has1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(q1[g * 4 + u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
+                }
+            }
+            if (has2) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(q2[g * 4 + u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
+                }
+            }
+        }
+        if (gap) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        const int swz_w = kVec == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
+    }
+    __syncwarp();
+    if (tr) tr[4] = clock64() - t_ref;
     __half* orow = a.out + out_coff + coff_add +
                    (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) * a.out_cstride;
 #pragma unroll

@@ -53,7 +53,7 @@ static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 1};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(W) * cstride * 2,
                              static_cast<cuuint64_t>(H) * W * cstride * 2};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 130, static_cast<cuuint32_t>(rows + 2), 1};  // rows = -1: one line (K2)
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 130, static_cast<cuuint32_t>(rows + 2), 1};  // rows = 0: two lines (K2)
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(ptr), dims, strides, box, estr,
@@ -355,14 +355,17 @@ int run_conv(Device& dev, const ConvCall& c) {
     }
     const bool roll_shape = c.out_mode == OUT_NHWC && c.nlayers == 1 && !c.dys && !c.dxs && c.rows == 0 && w.kc == 32 &&
                             (w.cout == 32 || w.cout == 64);
-    if (roll_shape && !(c.flags & FLAG_FORCE_TILE) && (dev.rolling || (c.flags & FLAG_FORCE_ROLL))) {
+    if (roll_shape && !(c.flags & FLAG_FORCE_TILE)) {
+        const int mask = (c.flags & FLAG_FORCE_ROLL) ? 7 : dev.rolling;
         CUtensorMap tm1;
-        rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, -1, w.kc, &tm1);
+        rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, 0, w.kc, &tm1);  // box of two input rows
         if (rc) return rc;
         rc = 1;
-        if (w.cout == 64) rc = launch_roll<64>(dev, tm1, a, w);            // whole layer resident
-        if (rc == 1 && w.wpack) rc = w.cout == 64 ? (w.wsplit ? launch_roll<32>(dev, tm1, a, w) : 1)  // two resident halves
-                                                  : launch_roll<32>(dev, tm1, a, w);
+        if (w.cout == 32 && (mask & 1)) rc = launch_roll<32>(dev, tm1, a, w);
+        if (w.cout == 64 && (mask & 2)) rc = launch_roll<64>(dev, tm1, a, w);                    // whole layer resident
+        if (w.cout == 64 && rc == 1 && (mask & 4) && w.wsplit &&
+            w.nchunks * RollTraits<64>::kBStage + RollTraits<64>::kMinSlots * RollTraits<64>::kASlot > RollTraits<64>::kBudget)
+            rc = launch_roll<32>(dev, tm1, a, w);                                               // two resident halves
         if (rc <= 0) return rc;
     }
     if (c.flags & FLAG_FORCE_ROLL) {

@@ -4,6 +4,7 @@
 #include "conv3x3_sm100.cuh"
 #include "vr_common.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -37,6 +38,8 @@ struct ScopedDev {
         }
         dev.sm_count = p.multiProcessorCount;
         if (const char* e = std::getenv("VR_WRES")) dev.weights_resident = std::atoi(e) != 0;
+        if (const char* e = std::getenv("VR_PDL")) dev.use_pdl = std::atoi(e) != 0;
+        if (const char* e = std::getenv("VR_ROLL")) dev.rolling = std::atoi(e);
         if (cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking) != cudaSuccess) {
             set_error(&err, "cudaStreamCreate failed");
             return;
@@ -98,6 +101,10 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
         VR_CUDA_CHECK(cudaMalloc(&dr2, h.size() * sizeof(__half)), dev.err);
         VR_CUDA_CHECK(cudaMemcpy(dr2, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
     }
+
+    // the uploads above ran on the legacy stream from pageable memory (the DMA may still be in flight when cudaMemcpy
+    // returns) and the conv runs on a non-blocking stream: order them explicitly
+    VR_CUDA_CHECK(cudaDeviceSynchronize(), dev.err);
 
     ConvCall c;
     c.in = dx;
@@ -208,8 +215,8 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
     c.rows = rows;
     c.flags = flags;
     long long* d_cyc = nullptr;
-    cudaMalloc(&d_cyc, 512 * sizeof(long long));
-    cudaMemset(d_cyc, 0, 512 * sizeof(long long));
+    cudaMalloc(&d_cyc, 1024 * sizeof(long long));
+    cudaMemset(d_cyc, 0, 1024 * sizeof(long long));
     c.dbg_cycles = d_cyc;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -227,8 +234,30 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         *ms_out = ms / iters;
-        long long hc[256];
+        long long hc[1024];
         cudaMemcpy(hc, d_cyc, sizeof(hc), cudaMemcpyDeviceToHost);
+        if (flags & FLAG_TRACE) {
+            // per owned box of issuer w: wait start, full landed, first MMA issue, commit issued (cycles since CTA start)
+            for (int i = 0; i < 32; ++i)
+                for (int w = 0; w < 2; ++w) {
+                    const long long* t = hc + 256 + w * 128 + i * 4;
+                    std::fprintf(stderr, "[trace] box %2d warp %d: wait@%lld full+%lld issue+%lld commit+%lld\n", 16 + 2 * i + w, w,
+                                 t[0], t[1] - t[0], t[2] - t[1], t[3] - t[2]);
+                }
+            std::fprintf(stderr, "[trace] CTA durations (cycles):");
+            for (int i = 0; i < 148; ++i) std::fprintf(stderr, "%s%lld", i % 10 == 0 ? "\n   " : " ", hc[i]);
+            std::fprintf(stderr, "\n");
+            std::fprintf(stderr, "[trace] CTA 0: prologue done @%lld, first MMA @%lld, issuers done @%lld / %lld, CTA end @%lld\n", hc[1003],
+                         hc[1000], hc[1001], hc[1002], hc[0]);
+            // epilogue warps 0 / 4 (lane quarter 0 of either row parity): wait start, accumulators ready, TMEM loaded,
+            // block re-initialised + released, staged in smem, stored to global
+            for (int i = 0; i < 16; ++i)
+                for (int w = 0; w < 2; ++w) {
+                    const long long* t = hc + 512 + w * 128 + i * 8;
+                    std::fprintf(stderr, "[etrace] row %2d group %d: wait@%lld ready+%lld ld+%lld release+%lld staged+%lld stored+%lld\n",
+                                 8 + 2 * i + w, w, t[0], t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
+                }
+        }
         long long mx = 0;
         for (int i = 0; i < 256; ++i) mx = hc[i] > mx ? hc[i] : mx;
         g_last_conv_cycles = mx;  // slowest CTA of the last launch

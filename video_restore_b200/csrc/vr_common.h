@@ -88,7 +88,11 @@ struct Device {
     bool multi_layer = false;
     bool fold_upsample = true;     // VR_FOLD_UP=0: materialise nearest x2 and run conv_up1/2 as plain 3x3 convs
     bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
-    bool rolling = true;  // VR_ROLL=0: never use the rolling-row kernel K2 (NHWC body layers run on the tiled kernel K1)
+    // VR_ROLL bit mask: which NHWC 3x3 layers run on the rolling-row kernel K2 instead of the tiled kernel K1:
+    // 1 = 32-channel outputs, 2 = 64-channel outputs whose weights fit (cin <= 128), 4 = 64-channel outputs as two halves
+    // Default 1: measured in-network (720p x4plus, interleaved A/B) -3.7 % frame time; the 64-channel classes are correct but
+    // not faster yet (resident 64 -> 64 is epilogue-bound, the split 192 -> 64 pays double activation reads).
+    int rolling = 1;
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc)
     std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
