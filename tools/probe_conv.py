@@ -117,11 +117,29 @@ def main():
         case("r-cin3", 12, 140, 3, 64, flags=R)
         case("r-big", 720, 1280, 64, 32, flags=R)         # 140 items, bands of 52 rows
         case("r-big-split", 300, 1280, 192, 64, res=2, flags=R)
+    elif group == "pair":
+        Pf = 512  # FLAG_FORCE_PAIR
+        case("p-basic", 8, 256, 32, 32, flags=Pf)
+        case("p-2chunk", 8, 128, 64, 32, flags=Pf)           # odd strip count: the pair's second strip is empty
+        case("p-tall", 75, 256, 64, 32, flags=Pf)            # mirrored ring (period 14) several times round
+        case("p-tall64", 75, 200, 64, 64, flags=Pf)          # period 6
+        case("p-multi", 37, 300, 64, 32, flags=Pf)
+        case("p-cin160", 40, 256, 160, 32, flags=Pf)
+        case("p-conv5", 41, 200, 192, 64, flags=Pf)          # 192 -> 64 resident as two 110 KB halves, N = 192
+        case("p-conv5-res2", 23, 140, 192, 64, res=2, flags=Pf)
+        case("p-lrelu", 12, 140, 64, 32, act=1, flags=Pf)
+        case("p-prelu", 12, 140, 64, 64, prelu=True, flags=Pf)
+        case("p-small", 5, 17, 64, 64, flags=Pf)
+        case("p-1row", 1, 33, 64, 32, flags=Pf)
+        case("p-2row", 2, 130, 96, 32, flags=Pf)
+        case("p-cin3", 12, 140, 3, 64, flags=Pf)
+        case("p-big", 720, 1280, 64, 32, flags=Pf)
+        case("p-big-conv5", 300, 1280, 192, 64, res=2, flags=Pf)
     elif group == "rbench":
         H, W = 720, 1280
         for cin, cout in [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64), (64, 64)]:
-            for label, rows, fl in (("K1", 4, 0), ("K2", 0, 128), ("K2-skip-epi", 0, 128 + 8), ("K2-skip-mma", 0, 128 + 4),
-                                    ("K2-skip-tma", 0, 128 + 2)):
+            for label, rows, fl in (("K1", 4, 0), ("K2", 0, 128), ("K2-skip-epi", 0, 128 + 8), ("K3", 0, 512),
+                                    ("K3-skip-epi", 0, 512 + 8), ("K3-skip-mma", 0, 512 + 4)):
                 try:
                     ms = _lib.conv3x3_bench(H, W, cin, cout, rows=rows, flags=fl, iters=20)
                     cyc = _lib.last_conv_cycles()

@@ -1,0 +1,374 @@
+// K3: paired rolling-row 3x3 convolution -- K2 (conv3x3_roll_sm100.cuh) on CTA PAIRS with tcgen05 cta_group::2.
+//
+// A cluster of two CTAs (two SMs of one TPC) owns two adjacent 128-pixel strips of one band of rows. The leader (cluster
+// rank 0) issues every MMA with M = 256: each CTA supplies the activations of ITS strip (A) and HALF of the weight rows (B)
+// at the same shared-memory offsets, and finds its strip's accumulators in its own TMEM (tools/mma2cta_probe). Per SM an
+// MMA therefore reads 4 KB of A but only half of B:
+//   * the dy-stacked N = 3 Cout MMA is tensor-bound for Cout = 32 as well (5.5 KB per 48 cycles instead of 7 KB);
+//   * a layer's weights take half the shared memory per CTA, so the 192 -> 64 layer (221 KB) is resident (110 KB per CTA)
+//     with full N = 192 MMAs -- no weight re-streaming per tile (K1) and no second pass over the activations (K2 halves).
+// The issue sequence has no special cases at all (with cta_group::2 a partial window would need a different B split):
+//   * PHANTOM rows: a band of `nrow` output rows is computed as nin2 + 2 "logical" rows (nin2 = its nrow + 2 input rows rounded
+//     up to even); input row j always updates logical rows j, j+1, j+2 with one full-window MMA per (chunk, dx, k16). The two
+//     logical rows before and the 2..3 after the band only collect partial sums and are discarded by the epilogue;
+//   * MIRRORED ring: logical row g lives at ring position m = g mod P, P = 512/Cout - 2, and the window of an input row is
+//     the three physical blocks starting at ITS first logical row's position -- never wrapping, because two spare physical
+//     blocks P, P+1 extend the ring. Rows with m < 2 therefore collect their first taps in block P + m and the rest in block
+//     m; the epilogue adds the two (mirror blocks restart from zero, ring blocks from the bias).
+// Synchronisation: each CTA's producer loads its own strip; both count their bytes on the LEADER's full barrier. The
+// leader's commits are multicast (slot release and accumulator-ready barriers exist in both CTAs); both CTAs' epilogue
+// warps arrive on the leader's accumulator-free barriers (remote mbarrier arrive). Warp roles as in K1 / K2.
+#pragma once
+#include "conv3x3_roll_sm100.cuh"
+
+namespace vr {
+
+constexpr int kPairMaxSlots = 8;
+
+template <int N>
+struct PairTraits {
+    static_assert(N == 32 || N == 64, "paired kernel: 32 or 64 output channels");
+    static constexpr int KC = 32;
+    static constexpr int kLineBytes = 130 * 64;                  // one input row of one channel chunk
+    static constexpr int kCopyBytes = 2 * kLineBytes;            // box = two input rows
+    static constexpr int kASlot = round_up_c(kCopyBytes, 512);
+    static constexpr int kWin = 3 * N;                           // MMA N: the dy taps of one input row
+    static constexpr int kBTap = (kWin / 2) * 64;                // this CTA's B rows of one (chunk, dx)
+    static constexpr int kBHalf = 3 * kBTap;                     // ... of one chunk: 9216 (N = 32) / 18432 (N = 64) bytes
+    static constexpr int kPhys = 512 / N;                        // physical ring blocks in TMEM
+    static constexpr int kPeriod = kPhys - 2;                    // logical ring period (two blocks are mirrors)
+    static constexpr int kStgBytes = kEpiWarps * 32 * N * 2;
+    static constexpr int kStatic = 3072;
+    static constexpr int kBudget = 227 * 1024 - 1024 - kStatic - kStgBytes;
+    static constexpr int kMinSlots = 3;
+    static_assert(kBTap % 512 == 0, "B tiles must keep the swizzle phase");
+};
+
+// The twelve MMAs of a box: (dx, k16) outer, the two input rows inner; one runtime base per operand, compile-time offsets.
+template <int N>
+__device__ __forceinline__ void pair_issue_box(uint32_t d0, uint32_t d1, uint32_t a_lo0, uint32_t b_lo0) {
+    using T = PairTraits<N>;
+    constexpr uint32_t kDescHi = ptx::kDescHiSw64;
+    constexpr uint32_t kIdesc = ptx::make_idesc_f16(256, T::kWin);
+    constexpr uint32_t kLine = T::kLineBytes >> 4;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const uint32_t ao = ((t >> 1) * 64 + (t & 1) * 32) >> 4, bo = ((t >> 1) * T::kBTap + (t & 1) * 32) >> 4;
+        ptx::umma_f16_pair(d0, a_lo0 + ao, kDescHi, b_lo0 + bo, kDescHi, kIdesc, 1u);
+        ptx::umma_f16_pair(d1, a_lo0 + kLine + ao, kDescHi, b_lo0 + bo, kDescHi, kIdesc, 1u);
+    }
+}
+
+// One output row x 32 pixels of this warp's lane quarter: accumulators (bias included; + mirror block when t_mir != ~0u) ->
+// activation -> residuals -> fp16 -> swizzled staging -> coalesced stores. Per 32-channel group, like epi_row_nhwc.
+template <int N>
+__device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main, uint32_t t_mir, uint32_t stg_s, int lane, int x_base,
+                                             int y, bool gap, const float* s_neg, int amode) {
+    constexpr int kVec = N / 8;
+    constexpr int kStgPitch = N * 2;
+    const int x = x_base + lane;
+    const bool inb = x < a.W;
+    const size_t p = static_cast<size_t>(y) * a.W + x;
+    const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
+    uint4 q1[kVec], q2[kVec];
+    if (inb && has1) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
+    }
+    if (inb && has2) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
+    }
+#pragma unroll
+    for (int g = 0; g < N / 32; ++g) {
+        float v[32];
+        if (t_mir != 0xffffffffu) {
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld32_issue(t_main + g * 32, r0);
+            ptx::tmem_ld32_issue(t_mir + g * 32, r1);
+            ptx::tmem_ld32_wait(r0);
+            ptx::tmem_ld32_wait(r1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        } else {
+            ptx::tmem_ld32(t_main + g * 32, v);
+        }
+        if (inb) {
+            if (amode == 1) {
+                const float sl = a.slope;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * sl);
+            } else if (amode == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + s_neg[g * 32 + j] * fminf(v[j], 0.f);
+            }
+            if (has1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(q1[g * 4 + u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
+                }
+            }
+            if (has2) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(q2[g * 4 + u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
+                }
+            }
+        }
+        if (gap) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        const int swz_w = kVec == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
+    }
+    __syncwarp();
+    __half* orow = a.out + a.out_coff +
+                   (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) * a.out_cstride;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int idx = i * 32 + lane;
+        const int px = idx / kVec, un = idx % kVec;
+        if (x_base + px < a.W) {
+            const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
+            const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
+            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
+        }
+    }
+    __syncwarp();
+}
+
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
+    using T = PairTraits<N>;
+    constexpr uint32_t P = T::kPeriod;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t s_bars[2 * kPairMaxSlots + 2 * P + 1];
+    __shared__ uint32_t s_tmem_slot;
+    __shared__ __align__(16) float s_bias[N];
+    __shared__ __align__(16) float s_neg[N];
+    uint64_t* full = s_bars;                  // leader: both CTAs' boxes of a slot have landed
+    uint64_t* empty = full + kPairMaxSlots;   // both: the MMAs reading the slot have retired (multicast commit)
+    uint64_t* tfull = empty + kPairMaxSlots;  // both: logical ring position complete (multicast commit)
+    uint64_t* tempty = tfull + P;             // leader: ring position drained and re-initialised in BOTH CTAs
+    uint64_t* wfull = tempty + P;
+    const int nslots = a.nstages;
+    const int nch = a.nchunks;
+    uint8_t* slot0 = smem + nch * T::kBHalf;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const long long t_start = clock64();
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPairMaxSlots; ++i) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], 1);
+        }
+        for (uint32_t i = 0; i < P; ++i) {
+            ptx::mbar_init(&tfull[i], kMmaWarps);   // both issuer warps commit (multicast) their MMAs of the row
+            ptx::mbar_init(&tempty[i], kEpiWarps);  // four lane-quarter warps in each of the two CTAs
+        }
+        ptx::mbar_init(wfull, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == kEpiWarps) {
+        if (lane == 0) ptx::prefetch_tmap(&tmap);
+        __syncwarp();
+        ptx::tmem_alloc_pair<512>(&s_tmem_slot);
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        s_bias[i] = (i < a.cout && a.bias) ? a.bias[i] : 0.f;
+        float neg = 1.f;
+        if (a.act == ACT_LRELU) neg = a.slope;
+        if (a.act == ACT_PRELU) neg = (i < a.cout && a.prelu) ? a.prelu[i] : 0.f;
+        s_neg[i] = neg;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = s_tmem_slot;
+    if (warp == kEpiWarps && lane == 0) {
+        // this CTA's half of the weight rows; weights are never written by a kernel: fetch before the dependency wait
+        const __half* wp = a.wpack + (static_cast<size_t>(rank) * nch) * (T::kBHalf / 2);
+        ptx::mbar_expect_tx(wfull, nch * T::kBHalf);
+        for (int c = 0; c < nch; ++c) ptx::bulk_load(smem + c * T::kBHalf, wp + static_cast<size_t>(c) * (T::kBHalf / 2), T::kBHalf, wfull);
+    }
+    if (warp < kEpiWarps) {
+        // ring blocks start as the bias row, mirror blocks as zero; every MMA accumulates
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+#pragma unroll
+        for (int g = 0; g < N / 32; ++g) {
+            float bz[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bz[j] = s_bias[g * 32 + j];
+            for (uint32_t blk = (warp >> 2) * (T::kPhys / 2); blk < (static_cast<uint32_t>(warp >> 2) + 1) * (T::kPhys / 2); ++blk) {
+                if (blk < P) ptx::tmem_st32(tmem_base + lane_base + blk * N + g * 32, bz);
+                else ptx::tmem_st32_zero(tmem_base + lane_base + blk * N + g * 32);
+            }
+        }
+        ptx::tmem_st_wait();
+    }
+    ptx::mbar_wait(wfull, 0);
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // both CTAs: barriers initialised, TMEM initialised, weight halves resident
+    ptx::tc_fence_after();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const int pairs_x = (a.tiles_x + 1) >> 1;
+    const int num_items = pairs_x * a.nbands;
+    const int cluster_id = static_cast<int>(blockIdx.x) >> 1, nclusters = static_cast<int>(gridDim.x) >> 1;
+
+    if (warp == kEpiWarps) {
+        // ===================== TMA producer: this CTA's strip; bytes counted on the leader's barrier =====================
+        if (lane == 0) {
+            const uint32_t lead_full = ptx::map_to_rank(&full[0], 0);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int item = cluster_id; item < num_items; item += nclusters) {
+                const int b = item / pairs_x, sx = (item - b * pairs_x) * 2 + static_cast<int>(rank);
+                const int y0 = a.y_begin + b * a.band;
+                const int nrow = (y0 + a.band < a.y_end ? y0 + a.band : a.y_end) - y0;
+                const int nin2 = (nrow + 3) & ~1;
+                for (int j0 = 0; j0 < nin2; j0 += 2) {
+                    for (int c = 0; c < nch; ++c) {
+                        ptx::mbar_wait(&empty[s], ph ^ 1);
+                        if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
+                        ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.cin_off + c * T::KC, sx * 128 - 1,
+                                              y0 - 1 + j0, 0);
+                        if (++s == nslots) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp > kEpiWarps) {
+        // ===================== MMA issuers: leader only (two warps alternating boxes) =====================
+        if (rank == 0) {
+            const int mw = warp - (kEpiWarps + 1);
+            int s = 0;
+            uint32_t ph = 0;
+            int gstage = 0;
+            uint32_t g0 = 0;  // logical rows started before the current item
+            for (int item = cluster_id; item < num_items; item += nclusters) {
+                const int b = item / pairs_x;
+                const int y0 = a.y_begin + b * a.band;
+                const int nrow = (y0 + a.band < a.y_end ? y0 + a.band : a.y_end) - y0;
+                const int nin2 = (nrow + 3) & ~1;
+                for (int j0 = 0; j0 < nin2; j0 += 2) {
+                    const uint32_t ga = g0 + j0;
+                    const uint32_t s0 = ga % P, s1 = (ga + 1) % P;
+                    for (int c = 0; c < nch; ++c) {
+                        const bool mine = (gstage & 1) == mw;
+                        if (mine) {
+                            ptx::mbar_wait(&full[s], ph);
+                            if (c == 0) {
+                                // logical rows first touched by this box: ga + 2, ga + 3 (and ga, ga + 1 at the top of an item)
+                                for (uint32_t gl = (j0 == 0 ? ga : ga + 2); gl < ga + 4; ++gl)
+                                    ptx::mbar_wait(&tempty[gl % P], ((gl / P) & 1u) ^ 1u);
+                            }
+                            ptx::tc_fence_after();
+                            if (gstage > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+                        }
+                        if (mine && ptx::elect_one()) {
+                            const uint32_t a_lo0 = ptx::smem_u32(slot0 + s * T::kASlot) >> 4;
+                            const uint32_t b_lo0 = ptx::smem_u32(smem + c * T::kBHalf) >> 4;
+                            if (!(a.flags & FLAG_SKIP_MMA)) pair_issue_box<N>(tmem_base + s0 * N, tmem_base + s1 * N, a_lo0, b_lo0);
+                            ptx::umma_commit_pair(&empty[s]);
+                        }
+                        __syncwarp();
+                        if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");
+                        ++gstage;
+                        if (++s == nslots) { s = 0; ph ^= 1; }
+                    }
+                    // logical rows ga, ga + 1 have their last tap (and the trailing phantom rows after the last box)
+                    if (ptx::elect_one()) {
+                        ptx::umma_commit_pair(&tfull[s0]);
+                        ptx::umma_commit_pair(&tfull[s1]);
+                        if (j0 + 2 >= nin2) {
+                            ptx::umma_commit_pair(&tfull[(ga + 2) % P]);
+                            ptx::umma_commit_pair(&tfull[(ga + 3) % P]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                g0 += nin2 + 2;
+            }
+            if (gstage > 0 && (gstage & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+        }
+    } else {
+        // ===================== epilogue warps 0..7 (both CTAs) =====================
+        const int quarter = warp & 3;
+        const uint32_t rgrp = warp >> 2;
+        const int amode = a.act == ACT_NONE ? 0 : ((a.act == ACT_LRELU && a.slope >= 0.f && a.slope <= 1.f) ? 1 : 2);
+        const uint32_t stg_s = ptx::smem_u32(slot0 + nslots * T::kASlot + warp * (32 * N * 2));
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t lead_tempty = ptx::map_to_rank(&tempty[0], 0);
+        uint32_t g0 = 0;
+        for (int item = cluster_id; item < num_items; item += nclusters) {
+            const int b = item / pairs_x, sx = (item - b * pairs_x) * 2 + static_cast<int>(rank);
+            const int y0 = a.y_begin + b * a.band;
+            const int nrow = (y0 + a.band < a.y_end ? y0 + a.band : a.y_end) - y0;
+            const int nin2 = (nrow + 3) & ~1;
+            const int lrows = nin2 + 2;
+            const int x_base = sx * 128 + quarter * 32;
+            const int x = x_base + lane;
+            bool xgap = false;
+            for (int j = 0; j < a.ngx; ++j) xgap |= ((x >> a.gshift) == a.gx[j]);
+#pragma unroll 1
+            for (int l = ((g0 & 1u) == rgrp ? 0 : 1); l < lrows; l += 2) {
+                const uint32_t gl = g0 + l;
+                const uint32_t m = gl % P;
+                ptx::mbar_wait(&tfull[m], (gl / P) & 1u);
+                ptx::tc_fence_after();
+                const uint32_t t_main = tmem_base + lane_base + m * N;
+                const uint32_t t_mir = m < 2 ? tmem_base + lane_base + (P + m) * N : 0xffffffffu;
+                if (l >= 2 && l < nrow + 2 && !(a.flags & FLAG_SKIP_EPI)) {
+                    const int y = y0 + l - 2;
+                    bool gap = xgap;
+                    for (int j = 0; j < a.ngy; ++j) gap |= ((y >> a.gshift) == a.gy[j]);
+                    epi_row_pair<N>(a, t_main, t_mir, stg_s, lane, x_base, y, gap, s_neg, amode);
+                }
+                // hand the position back: ring block = bias row, mirror block = 0
+#pragma unroll
+                for (int g = 0; g < N / 32; ++g) {
+                    float bz[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = *reinterpret_cast<const float4*>(s_bias + g * 32 + j * 4);
+                        bz[j * 4] = t.x; bz[j * 4 + 1] = t.y; bz[j * 4 + 2] = t.z; bz[j * 4 + 3] = t.w;
+                    }
+                    ptx::tmem_st32(t_main + g * 32, bz);
+                    if (m < 2) ptx::tmem_st32_zero(t_mir + g * 32);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(lead_tempty + m * 8);
+            }
+            g0 += lrows;
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // the peer may still be read (operands) or signalled (barriers) until both are done
+    if (warp == kEpiWarps) {
+        __syncwarp();
+        ptx::tmem_dealloc_pair<512>(tmem_base);
+    }
+    if (a.dbg_cycles && threadIdx.x == 0) a.dbg_cycles[blockIdx.x] = clock64() - t_start;
+}
+
+}  // namespace vr

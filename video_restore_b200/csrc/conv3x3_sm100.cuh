@@ -34,6 +34,7 @@ enum ConvFlags {
     FLAG_SKIP_TMA = 2, FLAG_SKIP_MMA = 4, FLAG_SKIP_EPI = 8, FLAG_SKIP_B = 16, FLAG_SKIP_A = 32,
     FLAG_FORCE_TILE = 64,  // kernel selection (tests): always the tiled kernel K1 ...
     FLAG_FORCE_ROLL = 128,  // ... or fail unless the rolling-row kernel K2 takes the layer
+    FLAG_FORCE_PAIR = 512,  // ... or the CTA-pair rolling-row kernel K3
     FLAG_TRACE = 256        // K2: CTA 0's issuers record per-box timestamps into dbg_cycles[256..512) (bench hook prints them)
 };
 

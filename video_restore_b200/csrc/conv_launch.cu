@@ -1,6 +1,6 @@
 // Host side of K1 / K2: weight repacking into the swizzled shared-memory image, TMA tensor-map construction,
 // kernel selection and launch. See conv3x3_sm100.cuh for the kernel.
-#include "conv3x3_roll_sm100.cuh"
+#include "conv3x3_pair_sm100.cuh"
 #include "vr_common.h"
 
 #include <cstdlib>
@@ -137,6 +137,22 @@ int pack_conv_weights(Device& dev, const float* w, const float* bias, const floa
                       dev.err);
         VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);
     }
+    if ((cout == 32 || cout == 64) && kc == 32) {
+        // K3 (CTA pairs): per (chunk, dx) the 3*cout dy-stacked rows are split between the two CTAs of a pair:
+        // [rank][chunk][dx][3*cout/2 rows][kc]; the swizzle phase of a row is unchanged (3*cout/2 is a multiple of 8)
+        std::vector<__half> pimg(elems);
+        const int half_rows = 3 * cout / 2;
+        for (int rank = 0; rank < 2; ++rank)
+            for (int c = 0; c < cw.nchunks; ++c)
+                for (int dx = 0; dx < 3; ++dx)
+                    std::memcpy(&pimg[((static_cast<size_t>(rank) * cw.nchunks + c) * 3 + dx) * half_rows * kc],
+                                &img[((static_cast<size_t>(c) * 9 + dx * 3) * cout + static_cast<size_t>(rank) * half_rows) * kc],
+                                static_cast<size_t>(half_rows) * kc * sizeof(__half));
+        VR_CUDA_CHECK(cudaMalloc(&cw.wpair, elems * sizeof(__half)), dev.err);
+        VR_CUDA_CHECK(cudaMemcpyAsync(cw.wpair, pimg.data(), elems * sizeof(__half), cudaMemcpyHostToDevice, dev.stream),
+                      dev.err);
+        VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);
+    }
     std::vector<float> b(cout, 0.f);
     if (bias) std::memcpy(b.data(), bias, cout * sizeof(float));
     VR_CUDA_CHECK(cudaMalloc(&cw.bias, cout * sizeof(float)), dev.err);
@@ -155,6 +171,7 @@ int pack_conv_weights(Device& dev, const float* w, const float* bias, const floa
 void free_conv_weights(ConvWeights* w) {
     if (w->wpack) cudaFree(w->wpack);
     if (w->wsplit) cudaFree(w->wsplit);
+    if (w->wpair) cudaFree(w->wpair);
     if (w->bias) cudaFree(w->bias);
     if (w->prelu) cudaFree(w->prelu);
     *w = ConvWeights();
@@ -263,6 +280,46 @@ static int launch_roll(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     return 0;
 }
 
+// K3: CTA pairs. returns 1 when the layer does not fit, 0 on launch, < 0 on error
+template <int N>
+static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const ConvWeights& w) {
+    using T = PairTraits<N>;
+    if (!w.wpair || w.cout != N) return 1;
+    const int w_bytes = w.nchunks * T::kBHalf;
+    int nslots = (T::kBudget - w_bytes) / T::kASlot;
+    if (nslots < T::kMinSlots) return 1;
+    if (nslots > kPairMaxSlots) nslots = kPairMaxSlots;
+    auto kern = conv3x3_pair_kernel<N>;
+    static bool attr_done[64] = {};
+    if (!attr_done[dev.ordinal & 63]) {
+        VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kBudget + T::kStgBytes + 1024),
+                      dev.err);
+        attr_done[dev.ordinal & 63] = true;
+    }
+    a.nsplit = 1;
+    a.wpack = w.wpair;
+    a.nstages = nslots;
+    a.tiles_x = (a.W + 127) / 128;
+    const int pairs_x = (a.tiles_x + 1) / 2;
+    const int max_clusters = dev.sm_count / 2;
+    choose_bands(pairs_x, a.y_end - a.y_begin, max_clusters, &a.band, &a.nbands);
+    const int items = pairs_x * a.nbands;
+    const int nclusters = items < max_clusters ? items : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nclusters);  // the kernel is compiled with __cluster_dims__(2, 1, 1)
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = w_bytes + nslots * T::kASlot + T::kStgBytes + 1024;
+    cfg.stream = dev.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = dev.use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
+    dev.launches++;
+    return 0;
+}
+
 int run_conv(Device& dev, const ConvCall& c) {
     const ConvWeights& w = c.nlayers > 1 ? *c.lw[c.nlayers - 1] : *c.w;  // the layer with the widest channel prefix
     if (c.nlayers > 1) {
@@ -356,11 +413,14 @@ int run_conv(Device& dev, const ConvCall& c) {
     const bool roll_shape = c.out_mode == OUT_NHWC && c.nlayers == 1 && !c.dys && !c.dxs && c.rows == 0 && w.kc == 32 &&
                             (w.cout == 32 || w.cout == 64);
     if (roll_shape && !(c.flags & FLAG_FORCE_TILE)) {
-        const int mask = (c.flags & FLAG_FORCE_ROLL) ? 7 : dev.rolling;
+        const int mask = (c.flags & FLAG_FORCE_PAIR) ? 24 : (c.flags & FLAG_FORCE_ROLL) ? 7 : dev.rolling;
         CUtensorMap tm1;
         rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, 0, w.kc, &tm1);  // box of two input rows
         if (rc) return rc;
         rc = 1;
+        if (w.cout == 32 && (mask & 8)) rc = launch_pair<32>(dev, tm1, a, w);
+        if (w.cout == 64 && (mask & 16)) rc = launch_pair<64>(dev, tm1, a, w);
+        if (rc <= 0) return rc;
         if (w.cout == 32 && (mask & 1)) rc = launch_roll<32>(dev, tm1, a, w);
         if (w.cout == 64 && (mask & 2)) rc = launch_roll<64>(dev, tm1, a, w);                    // whole layer resident
         if (w.cout == 64 && rc == 1 && (mask & 4) && w.wsplit &&
@@ -368,8 +428,8 @@ int run_conv(Device& dev, const ConvCall& c) {
             rc = launch_roll<32>(dev, tm1, a, w);                                               // two resident halves
         if (rc <= 0) return rc;
     }
-    if (c.flags & FLAG_FORCE_ROLL) {
-        set_error(dev.err, "run_conv: the rolling-row kernel does not take this layer");
+    if (c.flags & (FLAG_FORCE_ROLL | FLAG_FORCE_PAIR)) {
+        set_error(dev.err, "run_conv: the rolling-row kernels do not take this layer");
         return -1;
     }
     if (c.dys || c.dxs) {

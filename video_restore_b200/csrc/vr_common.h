@@ -32,6 +32,7 @@ struct ConvWeights {
     int nchunks = 0;  // ceil(cin / kc)
     __half* wpack = nullptr;  // device, [nchunks][dx][dy=2,1,0][npad][kc] swizzled
     __half* wsplit = nullptr; // device, cout == 64 only: the layer as two 32-channel halves [half][nchunks][tap][32][kc]
+    __half* wpair = nullptr;  // device, cout == 32 / 64: K3's per-CTA halves [rank][nchunks][dx][3*cout/2][kc]
     float* bias = nullptr;    // device [cout]
     float* prelu = nullptr;   // device [cout] or null
 };
@@ -89,7 +90,8 @@ struct Device {
     bool fold_upsample = true;     // VR_FOLD_UP=0: materialise nearest x2 and run conv_up1/2 as plain 3x3 convs
     bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
     // VR_ROLL bit mask: which NHWC 3x3 layers run on the rolling-row kernel K2 instead of the tiled kernel K1:
-    // 1 = 32-channel outputs, 2 = 64-channel outputs whose weights fit (cin <= 128), 4 = 64-channel outputs as two halves
+    // 1 = 32-channel outputs, 2 = 64-channel outputs whose weights fit (cin <= 128), 4 = 64-channel outputs as two halves;
+    // 8 / 16 = 32- / 64-channel outputs on the CTA-pair kernel K3 (takes precedence)
     // Default 1: measured in-network (720p x4plus, interleaved A/B) -3.7 % frame time; the 64-channel classes are correct but
     // not faster yet (resident 64 -> 64 is epilogue-bound, the split 192 -> 64 pays double activation reads).
     int rolling = 1;
