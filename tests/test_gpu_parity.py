@@ -21,7 +21,7 @@ CONV_ATOL, CONV_RTOL = 2e-2, 4e-3   # single conv, fp16 storage vs fp32 referenc
 # ----------------------------------------------------------------------------------------------------------
 # K1: single convolution against torch.nn.functional.conv2d (fp32, CPU)
 # ----------------------------------------------------------------------------------------------------------
-FORCE_TILE, FORCE_ROLL = 64, 128   # ConvFlags: kernel selection in the conv hook (K1 tiled / K2 rolling-row)
+FORCE_TILE, FORCE_ROLL, FORCE_PAIR = 64, 128, 512   # ConvFlags: kernel selection in the conv hook (K1 / K2 / K3)
 
 
 def _conv_case(gpu_lib, H, W, cin, cout, act=0, prelu=False, res=0, rows=0, seed=0, flags=0):
@@ -84,10 +84,30 @@ def test_conv_rolling_epilogues(gpu_lib, kw):
     _conv_case(gpu_lib, 23, 140, 192 if cout == 64 and "res" in kw else 64, cout, flags=FORCE_ROLL, **kw)
 
 
+# K3 (CTA-pair rolling-row kernel, tcgen05 cta_group::2): odd strip counts (empty second strip), mirrored ring several times
+# round (period 14 / 6), phantom rows around 1..3-row bands, the resident 192 -> 64 layer, many clusters
+@pytest.mark.parametrize("H,W,cin,cout", [(8, 256, 32, 32), (8, 128, 64, 32), (75, 256, 64, 32), (75, 200, 64, 64),
+                                          (37, 300, 64, 32), (40, 256, 160, 32), (41, 200, 192, 64), (5, 17, 64, 64),
+                                          (1, 33, 64, 32), (2, 130, 96, 32), (3, 129, 128, 32), (12, 140, 3, 64),
+                                          (12, 140, 12, 64), (131, 130, 64, 32), (300, 1280, 192, 64)])
+def test_conv_pair_shapes(gpu_lib, H, W, cin, cout):
+    _conv_case(gpu_lib, H, W, cin, cout, flags=FORCE_PAIR)
+
+
+@pytest.mark.parametrize("kw", [dict(act=1, cout=32), dict(prelu=True, cout=64), dict(prelu=True, cout=32), dict(res=1, cout=64),
+                                dict(res=2, cout=64), dict(res=2, cout=32, act=1)])
+def test_conv_pair_epilogues(gpu_lib, kw):
+    kw = dict(kw)
+    cout = kw.pop("cout")
+    _conv_case(gpu_lib, 23, 140, 192 if cout == 64 and "res" in kw else 64, cout, flags=FORCE_PAIR, **kw)
+
+
 def test_conv_rolling_rejects_other_layers(gpu_lib):
     from video_restore_b200._lib import VrError
     with pytest.raises(VrError):
         _conv_case(gpu_lib, 12, 140, 64, 3, flags=FORCE_ROLL)   # RGB output stays on K1
+    with pytest.raises(VrError):
+        _conv_case(gpu_lib, 12, 140, 64, 48, flags=FORCE_PAIR)  # pixel-shuffle output too
 
 
 @pytest.mark.parametrize("kw", [dict(act=1), dict(prelu=True), dict(res=1), dict(res=2), dict(act=1, rows=8)])
@@ -303,10 +323,10 @@ def test_full_size_480p_srvgg_crop_property(gpu_lib):
 
 def test_full_size_720p_x4plus_runs_and_is_tile_consistent(gpu_lib):
     """BASELINE configs[3] size. The oracle needs ~1 min/frame here, so parity at this size is checked through
-    properties: determinism, and crop-merge tiling vs single tile differing by <= 1 LSB on < 2 % of pixels
-    (tile borders only matter through zero padding 10+ px away; K2 sums an output row's taps in an
-    order that depends on the row's parity inside its band, so identical tile interiors can round differently in fp16:
-    0.5 % with K1 only, 1.2 % with K2 on the 32-channel layers)."""
+    properties: determinism, and crop-merge tiling vs single tile differing by <= 1 LSB on < 4 % of pixels
+    (tile borders only matter through zero padding 10+ px away; K2 / K3 sum an output row's taps in an
+    order that depends on the row's parity inside its band (and, in K3, on its ring position), so identical tile interiors
+    can round differently in fp16: 0.5 % with K1 only, 1.2 % with K2 on the 32-channel layers, 2.4 % with K3 everywhere)."""
     from video_restore_b200.restorer import FrameRestorer
 
     sd = random_state_dict("RealESRGAN_x4plus", seed=0)
@@ -319,7 +339,7 @@ def test_full_size_720p_x4plus_runs_and_is_tile_consistent(gpu_lib):
     b = tiled.process_frame(f)
     tiled.close()
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
-    assert a.shape == (2880, 5120, 3) and d.max() <= 1 and (d > 0).mean() < 2e-2
+    assert a.shape == (2880, 5120, 3) and d.max() <= 1 and (d > 0).mean() < 4e-2
     assert a.std() > 2.0
 
 
@@ -350,9 +370,9 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
     assert np.array_equal(base, multi) and n_multi < n_base
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_PDL": "0"})[0])
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_WRES": "0"})[0])
-    # K2 on its layer classes: deterministic and independent of PDL; against K1 the fp32 summation order differs (bias is the
+    # K2 / K3 on their layer classes: deterministic and independent of PDL; against K1 the fp32 summation order differs (bias is the
     # accumulator's initial value, taps are summed row by row), so the 8-bit frames agree within one level
-    for mask in ("1", "7"):
+    for mask in ("1", "7", "24", "31"):
         roll = run({"VR_ROLL": mask})[0]
         assert np.array_equal(roll, run({"VR_ROLL": mask})[0])
         assert np.array_equal(roll, run({"VR_ROLL": mask, "VR_PDL": "0"})[0])

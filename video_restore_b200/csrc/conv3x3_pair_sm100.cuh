@@ -37,7 +37,12 @@ struct PairTraits {
     static constexpr int kBHalf = 3 * kBTap;                     // ... of one chunk: 9216 (N = 32) / 18432 (N = 64) bytes
     static constexpr int kPhys = 512 / N;                        // physical ring blocks in TMEM
     static constexpr int kPeriod = kPhys - 2;                    // logical ring period (two blocks are mirrors)
-    static constexpr int kStgBytes = kEpiWarps * 32 * N * 2;
+    // 8 epilogue warps = two rows in flight. 16 warps (four rows, <= 107 registers, ~100 B of spills) were measured slower on every
+    // layer shape (e.g. 160 -> 32: 79.5 vs 67.6 us).
+    static constexpr int kEpi = 8;                               // epilogue warps
+    static constexpr int kGroups = kEpi / 4;                     // rows in flight
+    static constexpr int kThreads = (kEpi + 1 + kMmaWarps) * 32;
+    static constexpr int kStgBytes = kEpi * 32 * N * 2;
     static constexpr int kStatic = 3072;
     static constexpr int kBudget = 227 * 1024 - 1024 - kStatic - kStgBytes;
     static constexpr int kMinSlots = 3;
@@ -59,11 +64,32 @@ __device__ __forceinline__ void pair_issue_box(uint32_t d0, uint32_t d1, uint32_
     }
 }
 
+// Hand a ring position back: ring block <- bias row, mirror block <- 0, then arrive on the LEADER's barrier.
+template <int N>
+__device__ __forceinline__ void pair_release(uint32_t t_main, uint32_t t_mir, const float* s_bias, int lane, uint32_t release_addr) {
+#pragma unroll
+    for (int g = 0; g < N / 32; ++g) {
+        float bz[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(s_bias + g * 32 + j * 4);
+            bz[j * 4] = t.x; bz[j * 4 + 1] = t.y; bz[j * 4 + 2] = t.z; bz[j * 4 + 3] = t.w;
+        }
+        ptx::tmem_st32(t_main + g * 32, bz);
+        if (t_mir != 0xffffffffu) ptx::tmem_st32_zero(t_mir + g * 32);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive_cluster(release_addr);
+}
+
 // One output row x 32 pixels of this warp's lane quarter: accumulators (bias included; + mirror block when t_mir != ~0u) ->
 // activation -> residuals -> fp16 -> swizzled staging -> coalesced stores. Per 32-channel group, like epi_row_nhwc.
 template <int N>
 __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main, uint32_t t_mir, uint32_t stg_s, int lane, int x_base,
-                                             int y, bool gap, const float* s_neg, int amode) {
+                                             int y, bool gap, const float* s_bias, const float* s_neg, int amode,
+                                             uint32_t release_addr) {
     constexpr int kVec = N / 8;
     constexpr int kStgPitch = N * 2;
     const int x = x_base + lane;
@@ -81,10 +107,32 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
 #pragma unroll
         for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
     }
+    // N == 32: the whole row is loaded first and the ring position is handed back BEFORE the arithmetic and the stores (the
+    // remote arrive has cluster-scope release semantics: issued after the stores it would wait for them to drain).
+    // N == 64 (MMA-bound layers, twice the registers): per 32-channel group, position handed back by the caller afterwards.
+    constexpr bool kEarly = N == 32;
+    float v0[32];
+    if constexpr (kEarly) {
+        if (t_mir != 0xffffffffu) {
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld32_issue(t_main, r0);
+            ptx::tmem_ld32_issue(t_mir, r1);
+            ptx::tmem_ld32_wait(r0);
+            ptx::tmem_ld32_wait(r1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v0[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        } else {
+            ptx::tmem_ld32(t_main, v0);
+        }
+        pair_release<N>(t_main, t_mir, s_bias, lane, release_addr);
+    }
 #pragma unroll
     for (int g = 0; g < N / 32; ++g) {
         float v[32];
-        if (t_mir != 0xffffffffu) {
+        if constexpr (kEarly) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v0[j];
+        } else if (t_mir != 0xffffffffu) {
             uint32_t r0[32], r1[32];
             ptx::tmem_ld32_issue(t_main + g * 32, r0);
             ptx::tmem_ld32_issue(t_mir + g * 32, r1);
@@ -148,7 +196,7 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
 }
 
 template <int N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairTraits<N>::kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     using T = PairTraits<N>;
     constexpr uint32_t P = T::kPeriod;
@@ -179,12 +227,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
         }
         for (uint32_t i = 0; i < P; ++i) {
             ptx::mbar_init(&tfull[i], kMmaWarps);   // both issuer warps commit (multicast) their MMAs of the row
-            ptx::mbar_init(&tempty[i], kEpiWarps);  // four lane-quarter warps in each of the two CTAs
+            ptx::mbar_init(&tempty[i], 8);          // four lane-quarter warps in each of the two CTAs
         }
         ptx::mbar_init(wfull, 1);
         ptx::fence_mbar_init();
     }
-    if (warp == kEpiWarps) {
+    if (warp == T::kEpi) {
         if (lane == 0) ptx::prefetch_tmap(&tmap);
         __syncwarp();
         ptx::tmem_alloc_pair<512>(&s_tmem_slot);
@@ -200,13 +248,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_slot;
-    if (warp == kEpiWarps && lane == 0) {
+    if (warp == T::kEpi && lane == 0) {
         // this CTA's half of the weight rows; weights are never written by a kernel: fetch before the dependency wait
         const __half* wp = a.wpack + (static_cast<size_t>(rank) * nch) * (T::kBHalf / 2);
         ptx::mbar_expect_tx(wfull, nch * T::kBHalf);
         for (int c = 0; c < nch; ++c) ptx::bulk_load(smem + c * T::kBHalf, wp + static_cast<size_t>(c) * (T::kBHalf / 2), T::kBHalf, wfull);
     }
-    if (warp < kEpiWarps) {
+    if (warp < T::kEpi) {
         // ring blocks start as the bias row, mirror blocks as zero; every MMA accumulates
         const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
 #pragma unroll
@@ -214,7 +262,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             float bz[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) bz[j] = s_bias[g * 32 + j];
-            for (uint32_t blk = (warp >> 2) * (T::kPhys / 2); blk < (static_cast<uint32_t>(warp >> 2) + 1) * (T::kPhys / 2); ++blk) {
+            for (uint32_t blk = (warp >> 2) * (T::kPhys / T::kGroups); blk < (static_cast<uint32_t>(warp >> 2) + 1) * (T::kPhys / T::kGroups); ++blk) {
                 if (blk < P) ptx::tmem_st32(tmem_base + lane_base + blk * N + g * 32, bz);
                 else ptx::tmem_st32_zero(tmem_base + lane_base + blk * N + g * 32);
             }
@@ -232,7 +280,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
     const int num_items = pairs_x * a.nbands;
     const int cluster_id = static_cast<int>(blockIdx.x) >> 1, nclusters = static_cast<int>(gridDim.x) >> 1;
 
-    if (warp == kEpiWarps) {
+    if (warp == T::kEpi) {
         // ===================== TMA producer: this CTA's strip; bytes counted on the leader's barrier =====================
         if (lane == 0) {
             const uint32_t lead_full = ptx::map_to_rank(&full[0], 0);
@@ -254,10 +302,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                 }
             }
         }
-    } else if (warp > kEpiWarps) {
+    } else if (warp > T::kEpi) {
         // ===================== MMA issuers: leader only (two warps alternating boxes) =====================
         if (rank == 0) {
-            const int mw = warp - (kEpiWarps + 1);
+            const int mw = warp - (T::kEpi + 1);
             int s = 0;
             uint32_t ph = 0;
             int gstage = 0;
@@ -309,7 +357,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             if (gstage > 0 && (gstage & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
         }
     } else {
-        // ===================== epilogue warps 0..7 (both CTAs) =====================
+        // ===================== epilogue warps (both CTAs): warp % 4 = TMEM lane quarter, warp / 4 = row group =====================
         const int quarter = warp & 3;
         const uint32_t rgrp = warp >> 2;
         const int amode = a.act == ACT_NONE ? 0 : ((a.act == ACT_LRELU && a.slope >= 0.f && a.slope <= 1.f) ? 1 : 2);
@@ -328,35 +376,21 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             bool xgap = false;
             for (int j = 0; j < a.ngx; ++j) xgap |= ((x >> a.gshift) == a.gx[j]);
 #pragma unroll 1
-            for (int l = ((g0 & 1u) == rgrp ? 0 : 1); l < lrows; l += 2) {
+            for (int l = static_cast<int>((rgrp - g0) & (T::kGroups - 1)); l < lrows; l += T::kGroups) {
                 const uint32_t gl = g0 + l;
                 const uint32_t m = gl % P;
                 ptx::mbar_wait(&tfull[m], (gl / P) & 1u);
                 ptx::tc_fence_after();
                 const uint32_t t_main = tmem_base + lane_base + m * N;
                 const uint32_t t_mir = m < 2 ? tmem_base + lane_base + (P + m) * N : 0xffffffffu;
-                if (l >= 2 && l < nrow + 2 && !(a.flags & FLAG_SKIP_EPI)) {
+                const bool real = l >= 2 && l < nrow + 2 && !(a.flags & FLAG_SKIP_EPI);
+                if (real) {
                     const int y = y0 + l - 2;
                     bool gap = xgap;
                     for (int j = 0; j < a.ngy; ++j) gap |= ((y >> a.gshift) == a.gy[j]);
-                    epi_row_pair<N>(a, t_main, t_mir, stg_s, lane, x_base, y, gap, s_neg, amode);
+                    epi_row_pair<N>(a, t_main, t_mir, stg_s, lane, x_base, y, gap, s_bias, s_neg, amode, lead_tempty + m * 8);
                 }
-                // hand the position back: ring block = bias row, mirror block = 0
-#pragma unroll
-                for (int g = 0; g < N / 32; ++g) {
-                    float bz[32];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t = *reinterpret_cast<const float4*>(s_bias + g * 32 + j * 4);
-                        bz[j * 4] = t.x; bz[j * 4 + 1] = t.y; bz[j * 4 + 2] = t.z; bz[j * 4 + 3] = t.w;
-                    }
-                    ptx::tmem_st32(t_main + g * 32, bz);
-                    if (m < 2) ptx::tmem_st32_zero(t_mir + g * 32);
-                }
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(lead_tempty + m * 8);
+                if (!real || N != 32) pair_release<N>(t_main, t_mir, s_bias, lane, lead_tempty + m * 8);
             }
             g0 += lrows;
         }
@@ -364,7 +398,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
 
     ptx::tc_fence_before();
     ptx::cluster_sync();  // the peer may still be read (operands) or signalled (barriers) until both are done
-    if (warp == kEpiWarps) {
+    if (warp == T::kEpi) {
         __syncwarp();
         ptx::tmem_dealloc_pair<512>(tmem_base);
     }

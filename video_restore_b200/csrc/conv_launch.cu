@@ -307,7 +307,7 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     const int nclusters = items < max_clusters ? items : max_clusters;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters);  // the kernel is compiled with __cluster_dims__(2, 1, 1)
-    cfg.blockDim = dim3(kConvThreads);
+    cfg.blockDim = dim3(T::kThreads);
     cfg.dynamicSmemBytes = w_bytes + nslots * T::kASlot + T::kStgBytes + 1024;
     cfg.stream = dev.stream;
     cudaLaunchAttribute attr[1];

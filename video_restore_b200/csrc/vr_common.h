@@ -92,9 +92,9 @@ struct Device {
     // VR_ROLL bit mask: which NHWC 3x3 layers run on the rolling-row kernel K2 instead of the tiled kernel K1:
     // 1 = 32-channel outputs, 2 = 64-channel outputs whose weights fit (cin <= 128), 4 = 64-channel outputs as two halves;
     // 8 / 16 = 32- / 64-channel outputs on the CTA-pair kernel K3 (takes precedence)
-    // Default 1: measured in-network (720p x4plus, interleaved A/B) -3.7 % frame time; the 64-channel classes are correct but
-    // not faster yet (resident 64 -> 64 is epilogue-bound, the split 192 -> 64 pays double activation reads).
-    int rolling = 1;
+    // Default 24 + 7: K3 wherever it fits, else K2, else K1. Measured in-network (720p x4plus, interleaved A/B, sustained clocks):
+    // K1 only 42.7 ms, K2 on 32-channel layers 41.1 ms, K3 on 64-channel layers + K2 39.0 ms, K3 on both 36.9 ms.
+    int rolling = 31;
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc)
     std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
