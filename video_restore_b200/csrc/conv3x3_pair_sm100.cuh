@@ -303,58 +303,82 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             }
         }
     } else if (warp > T::kEpi) {
-        // ===================== MMA issuers: leader only (two warps alternating boxes) =====================
+        // ===================== MMA issuers: leader only =====================
+        // Two warps alternate UNITS of `a.unit` consecutive boxes (12 MMAs each). The owner of a unit first waits for every
+        // barrier the unit needs (operands landed, ring positions drained) while the other warp is still issuing, takes over
+        // through a named barrier, and then ONE elected lane walks the whole unit: nothing but address arithmetic between the
+        // MMAs. Both warps walk all boxes so that each can commit its own MMAs to the accumulator-ready barriers.
         if (rank == 0) {
             const int mw = warp - (T::kEpi + 1);
+            const int unit = a.unit < 1 ? 1 : a.unit;
+            const bool skip_mma = (a.flags & FLAG_SKIP_MMA) != 0;
             int s = 0;
             uint32_t ph = 0;
-            int gstage = 0;
+            int gunit = 0;
             uint32_t g0 = 0;  // logical rows started before the current item
             for (int item = cluster_id; item < num_items; item += nclusters) {
                 const int b = item / pairs_x;
                 const int y0 = a.y_begin + b * a.band;
                 const int nrow = (y0 + a.band < a.y_end ? y0 + a.band : a.y_end) - y0;
                 const int nin2 = (nrow + 3) & ~1;
-                for (int j0 = 0; j0 < nin2; j0 += 2) {
-                    const uint32_t ga = g0 + j0;
-                    const uint32_t s0 = ga % P, s1 = (ga + 1) % P;
-                    for (int c = 0; c < nch; ++c) {
-                        const bool mine = (gstage & 1) == mw;
-                        if (mine) {
-                            ptx::mbar_wait(&full[s], ph);
-                            if (c == 0) {
-                                // logical rows first touched by this box: ga + 2, ga + 3 (and ga, ga + 1 at the top of an item)
-                                for (uint32_t gl = (j0 == 0 ? ga : ga + 2); gl < ga + 4; ++gl)
+                const int nb = (nin2 >> 1) * nch;  // boxes of the item: row pairs x chunks, chunk fastest
+                int j0 = 0, c = 0;
+                for (int n = 0; n < nb; n += unit, ++gunit) {
+                    const int cnt = nb - n < unit ? nb - n : unit;
+                    const bool mine = (gunit & 1) == mw;
+                    if (mine) {
+                        int ss = s, cc = c, jj = j0;
+                        uint32_t pp = ph;
+                        for (int i = 0; i < cnt; ++i) {
+                            ptx::mbar_wait(&full[ss], pp);
+                            if (cc == 0) {
+                                // logical rows first touched by this row pair: ga + 2, ga + 3 (and ga, ga + 1 at the top of an item)
+                                const uint32_t ga = g0 + jj;
+                                for (uint32_t gl = (jj == 0 ? ga : ga + 2); gl < ga + 4; ++gl)
                                     ptx::mbar_wait(&tempty[gl % P], ((gl / P) & 1u) ^ 1u);
                             }
-                            ptx::tc_fence_after();
-                            if (gstage > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+                            if (++ss == nslots) { ss = 0; pp ^= 1; }
+                            if (++cc == nch) { cc = 0; jj += 2; }
                         }
-                        if (mine && ptx::elect_one()) {
-                            const uint32_t a_lo0 = ptx::smem_u32(slot0 + s * T::kASlot) >> 4;
-                            const uint32_t b_lo0 = ptx::smem_u32(smem + c * T::kBHalf) >> 4;
-                            if (!(a.flags & FLAG_SKIP_MMA)) pair_issue_box<N>(tmem_base + s0 * N, tmem_base + s1 * N, a_lo0, b_lo0);
-                            ptx::umma_commit_pair(&empty[s]);
-                        }
-                        __syncwarp();
-                        if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");
-                        ++gstage;
-                        if (++s == nslots) { s = 0; ph ^= 1; }
+                        ptx::tc_fence_after();
+                        if (gunit > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
                     }
-                    // logical rows ga, ga + 1 have their last tap (and the trailing phantom rows after the last box)
                     if (ptx::elect_one()) {
-                        ptx::umma_commit_pair(&tfull[s0]);
-                        ptx::umma_commit_pair(&tfull[s1]);
-                        if (j0 + 2 >= nin2) {
-                            ptx::umma_commit_pair(&tfull[(ga + 2) % P]);
-                            ptx::umma_commit_pair(&tfull[(ga + 3) % P]);
+                        int ss = s, cc = c, jj = j0;
+                        for (int i = 0; i < cnt; ++i) {
+                            const uint32_t ga = g0 + jj;
+                            const uint32_t s0 = ga % P, s1 = (ga + 1) % P;
+                            if (mine) {
+                                if (!skip_mma)
+                                    pair_issue_box<N>(tmem_base + s0 * N, tmem_base + s1 * N, ptx::smem_u32(slot0 + ss * T::kASlot) >> 4,
+                                                      ptx::smem_u32(smem + cc * T::kBHalf) >> 4);
+                                ptx::umma_commit_pair(&empty[ss]);
+                            }
+                            if (cc == nch - 1) {
+                                // logical rows ga, ga + 1 have their last tap (after the last row pair also the trailing phantom rows):
+                                // this warp's commits are one of the two arrivals on each barrier
+                                ptx::umma_commit_pair(&tfull[s0]);
+                                ptx::umma_commit_pair(&tfull[s1]);
+                                if (jj + 2 >= nin2) {
+                                    ptx::umma_commit_pair(&tfull[(ga + 2) % P]);
+                                    ptx::umma_commit_pair(&tfull[(ga + 3) % P]);
+                                }
+                            }
+                            if (++ss == nslots) ss = 0;
+                            if (++cc == nch) { cc = 0; jj += 2; }
                         }
                     }
                     __syncwarp();
+                    if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");
+                    for (int i = 0; i < cnt; ++i) {
+                        if (++s == nslots) { s = 0; ph ^= 1; }
+                        if (++c == nch) { c = 0; j0 += 2; }
+                    }
                 }
                 g0 += nin2 + 2;
             }
-            if (gstage > 0 && (gstage & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+            // the last unit's arrive has no matching sync: consume it so no named barrier is left half-arrived
+            if (gunit > 0 && (gunit & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
         }
     } else {
         // ===================== epilogue warps (both CTAs): warp % 4 = TMEM lane quarter, warp / 4 = row group =====================

@@ -88,6 +88,7 @@ struct ConvArgs {
     // Rolling-row kernel K2 (conv3x3_roll_sm100.cuh): work item = (band of `band` output rows, 128-pixel strip, channel half)
     int band, nbands;
     int nsplit;  // 1, or 2: the layer's 2N output channels are computed as two independent N-channel halves
+    int unit;    // K3: boxes per issuer hand-over
     long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 

@@ -299,6 +299,20 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     a.nsplit = 1;
     a.wpack = w.wpair;
     a.nstages = nslots;
+    {
+        // boxes per issuer hand-over: the next unit's operands should be landing while the current one executes
+        static const int env_unit = []() {
+            const char* e = std::getenv("VR_UNIT");
+            return e ? std::atoi(e) : 0;
+        }();
+        // 32 channels: up to three boxes (measured: 1 -> 2 boxes -7 %, 2 -> 3 within noise). 64 channels: the ring has only
+        // six logical positions, a row pair re-uses the positions of the row pair two before it, so a unit must never hold
+        // both (deadlock) and should not wait on rows the other warp is still producing: two boxes, one for single-chunk layers.
+        int u = N == 32 ? (nslots / 2 < 3 ? nslots / 2 : 3) : (w.nchunks >= 2 ? 2 : 1);
+        if (env_unit > 0 && (N == 32 || env_unit <= w.nchunks + 1)) u = env_unit;
+        if (u > nslots) u = nslots;
+        a.unit = u < 1 ? 1 : u;
+    }
     a.tiles_x = (a.W + 127) / 128;
     const int pairs_x = (a.tiles_x + 1) / 2;
     const int max_clusters = dev.sm_count / 2;
