@@ -55,10 +55,18 @@ static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int
                              static_cast<cuuint64_t>(H) * W * cstride * 2};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 130, static_cast<cuuint32_t>(rows + 2), 1};  // rows = 0: two lines (K2)
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    // VR_L2PROMO = 0 / 64 / 128 / 256 (default 128): L2 fetch granularity of the activation boxes (64 B per pixel and chunk)
+    static const CUtensorMapL2promotion l2_promo = []() {
+        const char* e = std::getenv("VR_L2PROMO");
+        const int v = e ? std::atoi(e) : 128;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                      : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     l2_promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error(dev.err, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) +
