@@ -162,6 +162,7 @@ def run_cpu_reference(wl, crop, steps, warmup):
 
 
 def main():
+    _saved_stdout_fd = None
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -211,6 +212,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # native libraries (NCCL's version banner) write to fd 1: keep stdout for the one JSON line
+        sys.stdout.flush()
+        _saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -339,6 +344,10 @@ def main():
         crop = args.cpu_crop or 256
         cfps, cdt, desc, cores = run_cpu_reference(wl, crop, 2, 1)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
+    if _saved_stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(_saved_stdout_fd, 1)
+        os.close(_saved_stdout_fd)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
