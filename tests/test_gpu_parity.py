@@ -102,6 +102,16 @@ def test_conv_pair_epilogues(gpu_lib, kw):
     _conv_case(gpu_lib, 23, 140, 192 if cout == 64 and "res" in kw else 64, cout, flags=FORCE_PAIR, **kw)
 
 
+@pytest.mark.parametrize("flags", [FORCE_ROLL, FORCE_PAIR])
+def test_conv_rolling_several_items_per_cta(gpu_lib, monkeypatch, flags):
+    """Grid capped at 6 CTAs (3 pairs): every CTA / pair walks several (band, strip) items, so the TMEM ring, the slot ring and
+    all barrier phases carry over from item to item (at frame sizes the grids are one item per CTA)."""
+    monkeypatch.setenv("VR_MAX_CTAS", "6")
+    _conv_case(gpu_lib, 97, 700, 96, 32, flags=flags)
+    _conv_case(gpu_lib, 61, 300, 192, 64, res=2, flags=flags)
+    _conv_case(gpu_lib, 50, 130, 64, 64, act=1, flags=flags)
+
+
 def test_conv_rolling_rejects_other_layers(gpu_lib):
     from video_restore_b200._lib import VrError
     with pytest.raises(VrError):

@@ -272,7 +272,9 @@ static int launch_roll(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     choose_bands(a.tiles_x * a.nsplit, a.y_end - a.y_begin, dev.sm_count, &a.band, &a.nbands);
     const int items = a.tiles_x * a.nbands * a.nsplit;
     int grid = items < dev.sm_count ? items : dev.sm_count;
+    if (dev.max_ctas > 0 && grid > dev.max_ctas) grid = dev.max_ctas;
     grid -= grid % a.nsplit;  // a CTA keeps one channel half resident
+    if (grid < a.nsplit) grid = a.nsplit;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kConvThreads);
@@ -326,7 +328,8 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     const int max_clusters = dev.sm_count / 2;
     choose_bands(pairs_x, a.y_end - a.y_begin, max_clusters, &a.band, &a.nbands);
     const int items = pairs_x * a.nbands;
-    const int nclusters = items < max_clusters ? items : max_clusters;
+    int nclusters = items < max_clusters ? items : max_clusters;
+    if (dev.max_ctas > 1 && nclusters > dev.max_ctas / 2) nclusters = dev.max_ctas / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters);  // the kernel is compiled with __cluster_dims__(2, 1, 1)
     cfg.blockDim = dim3(T::kThreads);

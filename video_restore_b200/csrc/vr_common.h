@@ -95,6 +95,7 @@ struct Device {
     // Default 24 + 7: K3 wherever it fits, else K2, else K1. Measured in-network (720p x4plus, interleaved A/B, sustained clocks):
     // K1 only 42.7 ms, K2 on 32-channel layers 41.1 ms, K3 on 64-channel layers + K2 39.0 ms, K3 on both 36.9 ms.
     int rolling = 31;
+    int max_ctas = 0;     // test hook (VR_MAX_CTAS): cap K2 / K3 grids so that a CTA / CTA pair walks several work items
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc)
     std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
