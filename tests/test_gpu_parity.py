@@ -22,6 +22,7 @@ CONV_ATOL, CONV_RTOL = 2e-2, 4e-3   # single conv, fp16 storage vs fp32 referenc
 # K1: single convolution against torch.nn.functional.conv2d (fp32, CPU)
 # ----------------------------------------------------------------------------------------------------------
 FORCE_TILE, FORCE_ROLL, FORCE_PAIR = 64, 128, 512   # ConvFlags: kernel selection in the conv hook (K1 / K2 / K3)
+PLANAR = 1024                                        # ... and chunk-planar source / residual / output tensors
 
 
 def _conv_case(gpu_lib, H, W, cin, cout, act=0, prelu=False, res=0, rows=0, seed=0, flags=0):
@@ -100,6 +101,21 @@ def test_conv_pair_epilogues(gpu_lib, kw):
     kw = dict(kw)
     cout = kw.pop("cout")
     _conv_case(gpu_lib, 23, 140, 192 if cout == 64 and "res" in kw else 64, cout, flags=FORCE_PAIR, **kw)
+
+
+@pytest.mark.parametrize("kernel", [FORCE_TILE, FORCE_ROLL, FORCE_PAIR])
+def test_conv_chunk_planar_tensors(gpu_lib, kernel):
+    """The network's activation layout: planes of 32 channels ([plane][H][W][32]); source prefix over several planes, output
+    into one or two planes, residuals read from planes (the hook converts to / from [H][W][C])."""
+    fl = kernel + PLANAR
+    _conv_case(gpu_lib, 37, 300, 64, 32, flags=fl)
+    _conv_case(gpu_lib, 40, 256, 160, 32, act=1, flags=fl)
+    _conv_case(gpu_lib, 41, 200, 192, 64, res=2, flags=fl)
+    _conv_case(gpu_lib, 23, 140, 64, 64, prelu=True, res=1, flags=fl)
+    _conv_case(gpu_lib, 12, 140, 3, 64, flags=fl)
+    if kernel == FORCE_TILE:
+        _conv_case(gpu_lib, 12, 140, 64, 3, flags=fl)      # RGB output from a planar source
+        _conv_case(gpu_lib, 12, 140, 64, 48, flags=fl)     # pixel shuffle + base
 
 
 @pytest.mark.parametrize("flags", [FORCE_ROLL, FORCE_PAIR])
@@ -382,6 +398,9 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_WRES": "0"})[0])
     # K2 / K3 on their layer classes: deterministic and independent of PDL; against K1 the fp32 summation order differs (bias is the
     # accumulator's initial value, taps are summed row by row), so the 8-bit frames agree within one level
+    # interleaved instead of chunk-planar activation tensors: same arithmetic in the same order
+    assert np.array_equal(base, run({"VR_ROLL": "0", "VR_PLANAR": "0"})[0])
+    assert np.array_equal(run({})[0], run({"VR_PLANAR": "0"})[0])
     for mask in ("1", "7", "24", "31"):
         roll = run({"VR_ROLL": mask})[0]
         assert np.array_equal(roll, run({"VR_ROLL": mask})[0])

@@ -135,6 +135,16 @@ def main():
         case("p-cin3", 12, 140, 3, 64, flags=Pf)
         case("p-big", 720, 1280, 64, 32, flags=Pf)
         case("p-big-conv5", 300, 1280, 192, 64, res=2, flags=Pf)
+    elif group == "planar":
+        for base, nm in ((64, "K1"), (128, "K2"), (512, "K3")):
+            fl = base + 1024
+            case(f"{nm}-pl-64-32", 37, 300, 64, 32, flags=fl)
+            case(f"{nm}-pl-160-32", 40, 256, 160, 32, act=1, flags=fl)
+            case(f"{nm}-pl-conv5", 41, 200, 192, 64, res=2, flags=fl)
+            case(f"{nm}-pl-64-64", 23, 140, 64, 64, prelu=True, res=1, flags=fl)
+            case(f"{nm}-pl-cin3", 12, 140, 3, 64, flags=fl)
+        case("K1-pl-rgb", 12, 140, 64, 3, flags=64 + 1024)
+        case("K1-pl-ps4", 12, 140, 64, 48, flags=64 + 1024)
     elif group == "rbench":
         H, W = 720, 1280
         for cin, cout in [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64), (64, 64)]:

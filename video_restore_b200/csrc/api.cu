@@ -139,35 +139,52 @@ const ConvWeights* layer(vr_handle* h, const std::string& name) {
 // conv helper
 // -------------------------------------------------------------------------------------------------
 struct Act {
-    __half* p;
-    int c;  // channels per pixel
+    __half* p = nullptr;
+    int c = 0;          // channels of the tensor
+    long long ps = 0;   // > 0: chunk-planar (planes of 32 channels, `ps` elements apart); 0: interleaved [pixel][c]
 };
+// Activation tensors with a multiple of 32 channels are chunk-planar (VR_PLANAR=0: interleaved, for A/B runs): every TMA box row
+// and every output row is then one contiguous run; the interleaved form costs the 32-channel layers 16..52 %.
+Act make_act(const vr_handle* h, void* ptr, int channels, size_t px) {
+    Act a;
+    a.p = static_cast<__half*>(ptr);
+    a.c = channels;
+    a.ps = (h->dev.planar && channels % 32 == 0) ? static_cast<long long>(px) * 32 : 0;
+    return a;
+}
 struct Rows {  // output row range of one launch (row-band scheduling); default = all rows
     int y0 = 0, y1 = -1;
 };
+void set_io(ConvCall& c, const Act& in, const Act& out) {
+    c.in = in.p;
+    c.in_cstride = in.ps ? 32 : in.c;
+    c.in_planes = in.ps ? in.c / 32 : 1;
+    c.in_pstride = in.ps;
+    c.out = out.p;
+    c.out_cstride = out.ps ? 32 : out.c;
+    c.out_pstride = out.ps;
+}
 
-int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act,
-         const __half* res1 = nullptr, int res1_c = 0, float s1 = 1.f, const __half* res2 = nullptr, int res2_c = 0,
-         float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr, int base_c = 0, Rows rows = Rows(),
-         int phase = -1) {
+int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act, Act res1 = Act(),
+         float s1 = 1.f, Act res2 = Act(), float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr,
+         int base_c = 0, Rows rows = Rows(), int phase = -1) {
     const ConvWeights* w = layer(h, name);
     if (!w) return fail(h, VR_E_STATE, "missing layer " + name);
     ConvCall c;
-    c.in = in.p;
-    c.in_cstride = in.c;
+    set_io(c, in, out);
     c.H = nh;
     c.W = nw;
     c.w = w;
     c.act = act;
     c.slope = 0.2f;
-    c.out = out.p;
-    c.out_cstride = out.c;
     c.out_coff = out_coff;
-    c.res1 = res1;
-    c.res1_cstride = res1_c;
+    c.res1 = res1.p;
+    c.res1_cstride = res1.ps ? 32 : res1.c;
+    c.res1_pstride = res1.ps;
     c.s1 = s1;
-    c.res2 = res2;
-    c.res2_cstride = res2_c;
+    c.res2 = res2.p;
+    c.res2_cstride = res2.ps ? 32 : res2.c;
+    c.res2_pstride = res2.ps;
     c.s2 = s2;
     c.out_mode = out_mode;
     c.base = base;
@@ -190,6 +207,13 @@ int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out,
         c.gy[i] = h->gaps.gy[i];
     }
     return run_conv(h->dev, c);
+}
+
+// nearest x2 of a whole activation tensor (only when VR_FOLD_UP=0): plane by plane for chunk-planar tensors
+int upsample2x_act(vr_handle* h, const Act& src, int H, int W, const Act& dst) {
+    if (!src.ps) return launch_upsample2x(h->dev, src.p, H, W, src.c, dst.p);
+    for (int k = 0; k < src.c / 32; ++k) VR_TRY(launch_upsample2x(h->dev, src.p + k * src.ps, H, W, 32, dst.p + k * dst.ps));
+    return 0;
 }
 
 // Optional row-band scheduling of the dense blocks (VR_BAND_MB = band working set in MB; default 0 = off).
@@ -220,12 +244,10 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
     VR_TRY(ensure(h, h->up1_out, px * 4 * 64 * 2));
     VR_TRY(ensure(h, h->up2_in, px * 16 * 64 * 2));
     VR_TRY(ensure(h, h->up2_out, px * 16 * 64 * 2));
-    Act in32{static_cast<__half*>(h->in32.p), 32};
-    Act feat{static_cast<__half*>(h->feat.p), 64};
-    Act trunk{static_cast<__half*>(h->trunk.p), 64};
-    Act rdb[3] = {{static_cast<__half*>(h->rdb[0].p), 192},
-                  {static_cast<__half*>(h->rdb[1].p), 192},
-                  {static_cast<__half*>(h->rdb[2].p), 192}};
+    Act in32 = make_act(h, h->in32.p, 32, px);
+    Act feat = make_act(h, h->feat.p, 64, px);
+    Act trunk = make_act(h, h->trunk.p, 64, px);
+    Act rdb[3] = {make_act(h, h->rdb[0].p, 192, px), make_act(h, h->rdb[1].p, 192, px), make_act(h, h->rdb[2].p, 192, px)};
     const int band = band_rows_for(nh, nw);
     // conv_first twice: once into `feat` (trunk residual), once into the first RDB buffer's x slot (K = 32: cheap)
     VR_TRY(conv(h, "conv_first", in32, nh, nw, feat, 0, ACT_NONE));
@@ -243,14 +265,11 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
                     // conv1..conv4 in ONE persistent launch: tiles of conv_{k+1} start as soon as the rows of conv_k
                     // they read are complete (no wave tail / pipeline refill between the four layers)
                     ConvCall mc;
-                    mc.in = X.p;
-                    mc.in_cstride = X.c;
+                    set_io(mc, X, X);
                     mc.H = nh;
                     mc.W = nw;
                     mc.act = ACT_LRELU;
                     mc.slope = 0.2f;
-                    mc.out = X.p;
-                    mc.out_cstride = X.c;
                     mc.nlayers = 4;
                     for (int k = 1; k <= 4; ++k) {
                         mc.lw[k - 1] = layer(h, pre + std::to_string(k));
@@ -268,46 +287,45 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
                 } else
                 for (int k = 1; k <= 4; ++k) {
                     const Rows rr{std::max(b0 - (5 - k), 0), std::min(b1 + (5 - k), nh)};
-                    VR_TRY(conv(h, pre + std::to_string(k), X, nh, nw, X, 64 + 32 * (k - 1), ACT_LRELU, nullptr, 0, 1.f,
-                                nullptr, 0, 1.f, OUT_NHWC, nullptr, 0, rr));
+                    VR_TRY(conv(h, pre + std::to_string(k), X, nh, nw, X, 64 + 32 * (k - 1), ACT_LRELU, Act(), 1.f, Act(), 1.f,
+                                OUT_NHWC, nullptr, 0, rr));
                 }
                 const Rows r5{b0, b1};
                 if (r < 2) {
-                    VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f, nullptr, 0, 1.f, OUT_NHWC,
-                                nullptr, 0, r5));  // x5*0.2 + x
+                    VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X, 0.2f, Act(), 1.f, OUT_NHWC, nullptr, 0,
+                                r5));  // x5*0.2 + x
                 } else {
                     // (x5*0.2 + x)*0.2 + rrdb_in ; rrdb_in lives in rdb[0][:, 0:64] and is overwritten in place
-                    VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X.p, 192, 0.2f, Y.p, 192, 0.2f, OUT_NHWC,
-                                nullptr, 0, r5));
+                    VR_TRY(conv(h, pre + "5", X, nh, nw, Y, 0, ACT_NONE, X, 0.2f, Y, 0.2f, OUT_NHWC, nullptr, 0, r5));
                 }
             }
         }
     }
-    VR_TRY(conv(h, "conv_body", rdb[0], nh, nw, trunk, 0, ACT_NONE, feat.p, 64, 1.0f));  // feat + body_feat
-    Act u1i{static_cast<__half*>(h->up1_in.p), 64}, u1o{static_cast<__half*>(h->up1_out.p), 64};
-    Act u2i{static_cast<__half*>(h->up2_in.p), 64}, u2o{static_cast<__half*>(h->up2_out.p), 64};
+    VR_TRY(conv(h, "conv_body", rdb[0], nh, nw, trunk, 0, ACT_NONE, feat, 1.0f));  // feat + body_feat
+    Act u1i = make_act(h, h->up1_in.p, 64, px * 4), u1o = make_act(h, h->up1_out.p, 64, px * 4);
+    Act u2i = make_act(h, h->up2_in.p, 64, px * 16), u2o = make_act(h, h->up2_out.p, 64, px * 16);
     if (h->dev.fold_upsample) {
         // lrelu(conv_up(nearest_x2(f))) as four 2x2-tap convs on f itself (one per output phase, pre-summed weights):
         // no upsampled tensor, 4/9 of the MACs
         for (int ph = 0; ph < 4; ++ph)
-            VR_TRY(conv(h, "conv_up1.phase" + std::to_string(ph), trunk, nh, nw, u1o, 0, ACT_LRELU, nullptr, 0, 1.f,
-                        nullptr, 0, 1.f, OUT_NHWC, nullptr, 0, Rows(), ph));
+            VR_TRY(conv(h, "conv_up1.phase" + std::to_string(ph), trunk, nh, nw, u1o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f,
+                        OUT_NHWC, nullptr, 0, Rows(), ph));
         h->gap_shift = 1;  // the phases of conv_up2 run on the 2x grid: gap columns / rows are 2 pixels wide there
         for (int ph = 0; ph < 4; ++ph)
-            VR_TRY(conv(h, "conv_up2.phase" + std::to_string(ph), u1o, 2 * nh, 2 * nw, u2o, 0, ACT_LRELU, nullptr, 0, 1.f,
-                        nullptr, 0, 1.f, OUT_NHWC, nullptr, 0, Rows(), ph));
+            VR_TRY(conv(h, "conv_up2.phase" + std::to_string(ph), u1o, 2 * nh, 2 * nw, u2o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f,
+                        OUT_NHWC, nullptr, 0, Rows(), ph));
         h->gap_shift = 2;
     } else {
-        VR_TRY(launch_upsample2x(h->dev, trunk.p, nh, nw, 64, u1i.p));
+        VR_TRY(upsample2x_act(h, trunk, nh, nw, u1i));
         h->gap_shift = 1;  // gap columns / rows are 2 pixels wide at 2x, 4 at 4x (nearest upsampling keeps them zero)
         VR_TRY(conv(h, "conv_up1", u1i, 2 * nh, 2 * nw, u1o, 0, ACT_LRELU));
-        VR_TRY(launch_upsample2x(h->dev, u1o.p, 2 * nh, 2 * nw, 64, u2i.p));
+        VR_TRY(upsample2x_act(h, u1o, 2 * nh, 2 * nw, u2i));
         h->gap_shift = 2;
         VR_TRY(conv(h, "conv_up2", u2i, 4 * nh, 4 * nw, u2o, 0, ACT_LRELU));
     }
     VR_TRY(conv(h, "conv_hr", u2o, 4 * nh, 4 * nw, u2i, 0, ACT_LRELU));  // up2_in is dead: reuse for conv_hr out
-    Act to{tile_out, 4};
-    VR_TRY(conv(h, "conv_last", u2i, 4 * nh, 4 * nw, to, 0, ACT_NONE, nullptr, 0, 1.f, nullptr, 0, 1.f, OUT_RGB4));
+    Act to = make_act(h, tile_out, 4, 0);
+    VR_TRY(conv(h, "conv_last", u2i, 4 * nh, 4 * nw, to, 0, ACT_NONE, Act(), 1.f, Act(), 1.f, OUT_RGB4));
     h->gap_shift = 0;
     return 0;
 }
@@ -317,16 +335,16 @@ int run_srvgg(vr_handle* h, int nh, int nw, __half* tile_out) {
     const size_t px = static_cast<size_t>(nh) * nw;
     VR_TRY(ensure(h, h->sv[0], px * 64 * 2));
     VR_TRY(ensure(h, h->sv[1], px * 64 * 2));
-    Act in32{static_cast<__half*>(h->in32.p), 32};
-    Act a{static_cast<__half*>(h->sv[0].p), 64}, b{static_cast<__half*>(h->sv[1].p), 64};
+    Act in32 = make_act(h, h->in32.p, 32, px);
+    Act a = make_act(h, h->sv[0].p, 64, px), b = make_act(h, h->sv[1].p, 64, px);
     VR_TRY(conv(h, "body.0", in32, nh, nw, a, 0, ACT_PRELU));
     for (int i = 0; i < h->cfg.num_conv; ++i) {
         VR_TRY(conv(h, "body." + std::to_string(2 * (i + 1)), a, nh, nw, b, 0, ACT_PRELU));
         std::swap(a, b);
     }
-    Act to{tile_out, 4};
-    VR_TRY(conv(h, "body." + std::to_string(2 * (h->cfg.num_conv + 1)), a, nh, nw, to, 0, ACT_NONE, nullptr, 0, 1.f,
-                nullptr, 0, 1.f, OUT_PS4, in32.p, 32));
+    Act to = make_act(h, tile_out, 4, 0);
+    VR_TRY(conv(h, "body." + std::to_string(2 * (h->cfg.num_conv + 1)), a, nh, nw, to, 0, ACT_NONE, Act(), 1.f, Act(), 1.f,
+                OUT_PS4, in32.p, 32));
     return 0;
 }
 
@@ -573,6 +591,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     h->dev.err = &h->err;
     if (const char* e = std::getenv("VR_PDL")) h->dev.use_pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_ROLL")) h->dev.rolling = std::atoi(e);
+    if (const char* e = std::getenv("VR_PLANAR")) h->dev.planar = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_WRES")) h->dev.weights_resident = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;

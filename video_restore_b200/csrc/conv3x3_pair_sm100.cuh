@@ -98,14 +98,14 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
     const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
     uint4 q1[kVec], q2[kVec];
     if (inb && has1) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff);
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
+        for (int j = 0; j < kVec; ++j)
+            q1[j] = __ldg(reinterpret_cast<const uint4*>(a.res1 + chan_off(p, a.res1_cstride, a.res1_pstride, a.res1_coff + j * 8)));
     }
     if (inb && has2) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff);
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
+        for (int j = 0; j < kVec; ++j)  // may alias `out` (in-place RRDB skip)
+            q2[j] = *reinterpret_cast<const uint4*>(a.res2 + chan_off(p, a.res2_cstride, a.res2_pstride, a.res2_coff + j * 8));
     }
     // N == 32: the whole row is loaded first and the ring position is handed back BEFORE the arithmetic and the stores (the
     // remote arrive has cluster-scope release semantics: issued after the stores it would wait for them to drain).
@@ -180,8 +180,9 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
         for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
     }
     __syncwarp();
-    __half* orow = a.out + a.out_coff +
-                   (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) * a.out_cstride;
+    // lane l always handles 16 B unit l % kVec of its pixels (32 % kVec == 0)
+    __half* orow = a.out + chan_off(static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx, a.out_cstride,
+                                    a.out_pstride, a.out_coff + (lane % kVec) * 8);
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
         const int idx = i * 32 + lane;
@@ -189,7 +190,7 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
         if (x_base + px < a.W) {
             const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
             const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
-            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
+            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride) = val;
         }
     }
     __syncwarp();
@@ -295,8 +296,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                     for (int c = 0; c < nch; ++c) {
                         ptx::mbar_wait(&empty[s], ph ^ 1);
                         if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
-                        ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.cin_off + c * T::KC, sx * 128 - 1,
-                                              y0 - 1 + j0, 0);
+                        const int ch0 = a.cin_off + c * T::KC;
+                        ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0, sx * 128 - 1,
+                                              y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0);
                         if (++s == nslots) { s = 0; ph ^= 1; }
                     }
                 }

@@ -203,8 +203,9 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                             ptx::mbar_arrive(&full[s]);
                         } else {
                             ptx::mbar_expect_tx(&full[s], T::kCopyBytes);
-                            ptx::tma_load_4d(slot0 + s * T::kASlot, &tmap, &full[s], a.cin_off + c * T::KC, sx * 128 - 1,
-                                             y0 - 1 + j, 0);
+                            const int ch0 = a.cin_off + c * T::KC;
+                            ptx::tma_load_4d(slot0 + s * T::kASlot, &tmap, &full[s], a.in_cstride == 32 ? 0 : ch0, sx * 128 - 1,
+                                             y0 - 1 + j, a.in_cstride == 32 ? ch0 >> 5 : 0);
                         }
                         if (++s == nslots) { s = 0; ph ^= 1; }
                     }

@@ -35,6 +35,7 @@ enum ConvFlags {
     FLAG_FORCE_TILE = 64,  // kernel selection (tests): always the tiled kernel K1 ...
     FLAG_FORCE_ROLL = 128,  // ... or fail unless the rolling-row kernel K2 takes the layer
     FLAG_FORCE_PAIR = 512,  // ... or the CTA-pair rolling-row kernel K3
+    FLAG_PLANAR = 1024,     // conv test hook: run the layer on chunk-planar tensors
     FLAG_TRACE = 256        // K2: CTA 0's issuers record per-box timestamps into dbg_cycles[256..512) (bench hook prints them)
 };
 
@@ -44,6 +45,7 @@ struct ConvArgs {
     int tiles_x, tiles_y;  // ceil(W/128), ceil((y_end - y_begin)/TH)
     int nchunks;           // Cin_padded / KC
     int cin_off;           // first input channel inside the source buffer
+    int in_cstride;        // source channels per pixel (per plane); 32 = chunk-planar tensor (see chan_off)
     const __half* wpack;   // [nchunks][dx][dy=2,1,0][N][32] fp16, pre-swizzled smem image
     const float* bias;     // [cout]
     const float* prelu;    // [cout] or null
@@ -51,6 +53,10 @@ struct ConvArgs {
     float slope;
     __half* out;
     int out_cstride, out_coff, cout;
+    // Chunk-planar tensors: a tensor with cstride == 32 stores channels [32k, 32k+32) as plane k, [H][W][32] fp16, planes
+    // `pstride` elements apart (every TMA box row and every output row is then contiguous; the interleaved [H][W][C] form
+    // costs the 32-channel layers 16..52 %). Any other cstride is the interleaved form (pstride unused).
+    long long out_pstride, res1_pstride, res2_pstride;
     const __half* res1;
     int res1_cstride, res1_coff;
     float s1;
@@ -131,6 +137,11 @@ struct ConvTraits {
     static_assert(TH % 2 == 0, "rows alternate between the two epilogue groups");
 };
 
+// element offset of channel `ch` of pixel `p`: chunk-planar when cs == 32, interleaved [pixel][cs] otherwise
+__device__ __forceinline__ size_t chan_off(size_t p, int cs, long long ps, int ch) {
+    return cs == 32 ? static_cast<size_t>(ch >> 5) * static_cast<size_t>(ps) + p * 32 + (ch & 31) : p * static_cast<size_t>(cs) + ch;
+}
+
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
@@ -187,14 +198,16 @@ __device__ __forceinline__ void epi_row_nhwc(const ConvArgs& a, uint32_t t_addr,
     const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
     uint4 q1[kVec], q2[kVec];
     if (inb && has1) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff + coff_add);
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
+        for (int j = 0; j < kVec; ++j)
+            q1[j] = __ldg(reinterpret_cast<const uint4*>(
+                a.res1 + chan_off(p, a.res1_cstride, a.res1_pstride, a.res1_coff + coff_add + j * 8)));
     }
     if (inb && has2) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff + coff_add);
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
+        for (int j = 0; j < kVec; ++j)  // may alias `out` (in-place RRDB skip)
+            q2[j] = *reinterpret_cast<const uint4*>(
+                a.res2 + chan_off(p, a.res2_cstride, a.res2_pstride, a.res2_coff + coff_add + j * 8));
     }
 #pragma unroll
     for (int g = 0; g < N / 32; ++g) {
@@ -232,8 +245,9 @@ __device__ __forceinline__ void epi_row_nhwc(const ConvArgs& a, uint32_t t_addr,
         for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
     }
     __syncwarp();
-    __half* orow = a.out + out_coff + coff_add +
-                   (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) * a.out_cstride;
+    // lane l always handles 16 B unit l % kVec of its pixels (32 % kVec == 0)
+    __half* orow = a.out + chan_off(static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx, a.out_cstride,
+                                    a.out_pstride, out_coff + coff_add + (lane % kVec) * 8);
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
         const int idx = i * 32 + lane;
@@ -241,7 +255,7 @@ __device__ __forceinline__ void epi_row_nhwc(const ConvArgs& a, uint32_t t_addr,
         if (x_base + px < a.W) {
             const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
             const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
-            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
+            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride) = val;
         }
     }
     __syncwarp();
@@ -263,14 +277,16 @@ __device__ __forceinline__ void epi_row_nhwc_folded(const ConvArgs& a, uint32_t 
     const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
     uint4 q1[kVec], q2[kVec];
     if (inb && has1) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res1 + p * a.res1_cstride + a.res1_coff + coff_add);
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) q1[j] = __ldg(rp + j);
+        for (int j = 0; j < kVec; ++j)
+            q1[j] = __ldg(reinterpret_cast<const uint4*>(
+                a.res1 + chan_off(p, a.res1_cstride, a.res1_pstride, a.res1_coff + coff_add + j * 8)));
     }
     if (inb && has2) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res2 + p * a.res2_cstride + a.res2_coff + coff_add);
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) q2[j] = rp[j];  // may alias `out` (in-place RRDB skip)
+        for (int j = 0; j < kVec; ++j)  // may alias `out` (in-place RRDB skip)
+            q2[j] = *reinterpret_cast<const uint4*>(
+                a.res2 + chan_off(p, a.res2_cstride, a.res2_pstride, a.res2_coff + coff_add + j * 8));
     }
     uint32_t raw[N];
 #pragma unroll
@@ -339,8 +355,9 @@ __device__ __forceinline__ void epi_row_nhwc_folded(const ConvArgs& a, uint32_t 
     }
     __syncwarp();
     if (tr) tr[4] = clock64() - t_ref;
-    __half* orow = a.out + out_coff + coff_add +
-                   (static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx) * a.out_cstride;
+    // lane l always handles 16 B unit l % kVec of its pixels (32 % kVec == 0)
+    __half* orow = a.out + chan_off(static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx, a.out_cstride,
+                                    a.out_pstride, out_coff + coff_add + (lane % kVec) * 8);
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
         const int idx = i * 32 + lane;
@@ -348,7 +365,7 @@ __device__ __forceinline__ void epi_row_nhwc_folded(const ConvArgs& a, uint32_t 
         if (x_base + px < a.W) {
             const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
             const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
-            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride + un * 8) = val;
+            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride) = val;
         }
     }
     __syncwarp();
@@ -497,7 +514,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                     } else {
                         const bool ld_a = !(a.flags & FLAG_SKIP_A), ld_b = !(a.flags & FLAG_SKIP_B) && !a.wres;
                         ptx::mbar_expect_tx(&full[s], (ld_a ? T::kCopyBytes : 0) + (ld_b ? T::kBBytes : 0));
-                        if (ld_a) ptx::tma_load_4d(st, &tmap, &full[s], a.cin_off + c * KC, x0 - 1, y0 - 1, 0);
+                        const int ch0 = a.cin_off + c * KC;
+                        if (ld_a)
+                            ptx::tma_load_4d(st, &tmap, &full[s], a.in_cstride == 32 ? 0 : ch0, x0 - 1, y0 - 1,
+                                             a.in_cstride == 32 ? ch0 >> 5 : 0);
                         if (ld_b)
                             ptx::bulk_load(st + T::kAStage, wp + static_cast<size_t>(c) * 9 * N * KC, T::kBBytes, &full[s]);
                     }

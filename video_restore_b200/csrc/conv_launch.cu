@@ -40,9 +40,12 @@ static EncodeTiledFn get_encode_fn(std::string* err) {
 }
 
 // NHWC fp16 activation tensor as a 4-D map (C, W, H, 1); box = 32 channels x pitch pixels x (rows + 2) lines.
-static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int H, int rows, int kc,
-                         CUtensorMap* out) {
-    auto key = std::make_tuple(static_cast<const void*>(ptr), cstride, W, H, rows, kc);
+// Chunk-planar tensors (cstride 32): the fourth dimension walks the planes.
+static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int H, int rows, int kc, int planes,
+                         long long pstride, CUtensorMap* out) {
+    if (planes < 1) planes = 1;
+    if (planes == 1) pstride = static_cast<long long>(H) * W * cstride;
+    auto key = std::make_tuple(static_cast<const void*>(ptr), cstride, W, H, rows, kc, planes, pstride);
     auto it = dev.tmaps.find(key);
     if (it != dev.tmaps.end()) {
         *out = it->second;
@@ -50,9 +53,10 @@ static int make_act_tmap(Device& dev, const __half* ptr, int cstride, int W, int
     }
     EncodeTiledFn enc = get_encode_fn(dev.err);
     if (!enc) return -2;
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 1};
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                          static_cast<cuuint64_t>(planes)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(cstride) * 2, static_cast<cuuint64_t>(W) * cstride * 2,
-                             static_cast<cuuint64_t>(H) * W * cstride * 2};
+                             static_cast<cuuint64_t>(pstride) * 2};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), 130, static_cast<cuuint32_t>(rows + 2), 1};  // rows = 0: two lines (K2)
     cuuint32_t estr[4] = {1, 1, 1, 1};
     // VR_L2PROMO = 0 / 64 / 128 / 256 (default 128): L2 fetch granularity of the activation boxes (64 B per pixel and chunk)
@@ -362,7 +366,11 @@ int run_conv(Device& dev, const ConvCall& c) {
     int rows = c.rows;
     if (rows == 0) rows = 4;
     CUtensorMap tm;
-    int rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, rows, w.kc, &tm);
+    if (c.in_cstride == 32 && (c.cin_off % 32 != 0 || (c.cin_off + w.nchunks * w.kc + 31) / 32 > c.in_planes)) {
+        set_error(dev.err, "run_conv: chunk-planar source needs a 32-aligned channel prefix inside its planes");
+        return -1;
+    }
+    int rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, rows, w.kc, c.in_planes, c.in_pstride, &tm);
     if (rc) return rc;
     ConvArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -373,6 +381,10 @@ int run_conv(Device& dev, const ConvCall& c) {
     if (a.y_end <= a.y_begin) return 0;
     a.nchunks = w.nchunks;
     a.cin_off = c.cin_off;
+    a.in_cstride = c.in_cstride;
+    a.out_pstride = c.out_pstride;
+    a.res1_pstride = c.res1_pstride;
+    a.res2_pstride = c.res2_pstride;
     a.wpack = w.wpack;
     a.bias = w.bias;
     a.prelu = w.prelu;
@@ -440,7 +452,7 @@ int run_conv(Device& dev, const ConvCall& c) {
     if (roll_shape && !(c.flags & FLAG_FORCE_TILE)) {
         const int mask = (c.flags & FLAG_FORCE_PAIR) ? 24 : (c.flags & FLAG_FORCE_ROLL) ? 7 : dev.rolling;
         CUtensorMap tm1;
-        rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, 0, w.kc, &tm1);  // box of two input rows
+        rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, 0, w.kc, c.in_planes, c.in_pstride, &tm1);  // two input rows
         if (rc) return rc;
         rc = 1;
         if (w.cout == 32 && (mask & 8)) rc = launch_pair<32>(dev, tm1, a, w);

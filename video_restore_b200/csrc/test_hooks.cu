@@ -52,10 +52,12 @@ struct ScopedDev {
     }
 };
 
-std::vector<__half> to_half_padded(const float* x, size_t px, int c, int cpad) {
+// [px][c] fp32 -> fp16 [px][cpad], or chunk-planar [cpad/32][px][32] (FLAG_PLANAR)
+std::vector<__half> to_half_padded(const float* x, size_t px, int c, int cpad, bool planar = false) {
     std::vector<__half> h(px * cpad, __float2half(0.f));
     for (size_t p = 0; p < px; ++p)
-        for (int i = 0; i < c; ++i) h[p * cpad + i] = __float2half_rn(x[p * c + i]);
+        for (int i = 0; i < c; ++i)
+            h[planar ? (static_cast<size_t>(i >> 5) * px + p) * 32 + (i & 31) : p * cpad + i] = __float2half_rn(x[p * c + i]);
     return h;
 }
 }  // namespace
@@ -79,7 +81,10 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     int rc = pack_conv_weights(dev, t->weight, t->bias, t->act == ACT_PRELU ? t->prelu : nullptr, t->cin, cout, &w);
     if (rc) return rc;
 
-    std::vector<__half> hx = to_half_padded(t->x, px, t->cin, cin_pad);
+    // FLAG_PLANAR: source, residuals and (NHWC, cout % 32 == 0) output as chunk-planar tensors, as the network uses them
+    const bool planar = (t->flags & FLAG_PLANAR) != 0;
+    const bool out_planar = planar && !rgb4 && !ps4 && cout % 32 == 0;
+    std::vector<__half> hx = to_half_padded(t->x, px, t->cin, cin_pad, planar);
     __half *dx = nullptr, *dy = nullptr, *dr1 = nullptr, *dr2 = nullptr;
     const size_t out_elems = ps4 ? px * 16 * 4 : px * out_c;
     VR_CUDA_CHECK(cudaMalloc(&dx, hx.size() * sizeof(__half)), dev.err);
@@ -93,12 +98,12 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     VR_CUDA_CHECK(cudaMemset(dy, 0, out_elems * sizeof(__half)), dev.err);
     VR_CUDA_CHECK(cudaMemcpy(dx, hx.data(), hx.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
     if (t->res1) {
-        std::vector<__half> h = to_half_padded(t->res1, px, cout, cout);
+        std::vector<__half> h = to_half_padded(t->res1, px, cout, cout, out_planar);
         VR_CUDA_CHECK(cudaMalloc(&dr1, h.size() * sizeof(__half)), dev.err);
         VR_CUDA_CHECK(cudaMemcpy(dr1, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
     }
     if (t->res2) {
-        std::vector<__half> h = to_half_padded(t->res2, px, cout, cout);
+        std::vector<__half> h = to_half_padded(t->res2, px, cout, cout, out_planar);
         VR_CUDA_CHECK(cudaMalloc(&dr2, h.size() * sizeof(__half)), dev.err);
         VR_CUDA_CHECK(cudaMemcpy(dr2, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
     }
@@ -109,24 +114,29 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
 
     ConvCall c;
     c.in = dx;
-    c.in_cstride = cin_pad;
+    c.in_cstride = planar ? 32 : cin_pad;
+    c.in_planes = planar ? cin_pad / 32 : 1;
+    c.in_pstride = static_cast<long long>(px) * 32;
     c.H = t->H;
     c.W = t->W;
     c.w = &w;
     c.act = t->act;
     c.slope = t->slope;
     c.out = dy;
-    c.out_cstride = out_c;
+    c.out_cstride = out_planar ? 32 : out_c;
+    c.out_pstride = static_cast<long long>(px) * 32;
     c.out_coff = 0;
     c.res1 = dr1;
-    c.res1_cstride = cout;
+    c.res1_cstride = out_planar ? 32 : cout;
+    c.res1_pstride = static_cast<long long>(px) * 32;
     c.s1 = t->s1;
     c.res2 = dr2;
-    c.res2_cstride = cout;
+    c.res2_cstride = out_planar ? 32 : cout;
+    c.res2_pstride = static_cast<long long>(px) * 32;
     c.s2 = t->s2;
     c.out_mode = rgb4 ? OUT_RGB4 : (ps4 ? OUT_PS4 : OUT_NHWC);
     c.base = dx;
-    c.base_cstride = cin_pad;
+    c.base_cstride = planar ? 32 : cin_pad;
     c.rows = t->rows;
     c.flags = t->flags;
 
@@ -169,7 +179,9 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
                 for (int ch = 0; ch < 3; ++ch) t->y[i * 3 + ch] = __half2float(hy[i * 4 + ch]);
         } else {
             for (size_t p = 0; p < px; ++p)
-                for (int ch = 0; ch < cout; ++ch) t->y[p * cout + ch] = __half2float(hy[p * out_c + ch]);
+                for (int ch = 0; ch < cout; ++ch)
+                    t->y[p * cout + ch] =
+                        __half2float(hy[out_planar ? (static_cast<size_t>(ch >> 5) * px + p) * 32 + (ch & 31) : p * out_c + ch]);
         }
     }
     cudaEventDestroy(e0);
@@ -188,7 +200,9 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
     if (!sd.ok) return VR_E_NODEVICE;
     Device& dev = sd.dev;
     const size_t px = static_cast<size_t>(H) * W;
-    const int cin_pad = (cin + 31) / 32 * 32;
+    int cin_pad = (cin + 31) / 32 * 32;
+    // VR_BENCH_CSTRIDE: time the layer on a wider interleaved source buffer (the network's 192-channel dense-block buffers)
+    if (const char* e = std::getenv("VR_BENCH_CSTRIDE")) cin_pad = std::atoi(e) > cin_pad ? std::atoi(e) : cin_pad;
     std::vector<float> w(static_cast<size_t>(cout) * cin * 9);
     uint32_t s = 12345u;
     for (auto& v : w) {
@@ -199,7 +213,8 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
     int rc = pack_conv_weights(dev, w.data(), nullptr, nullptr, cin, cout, &cw);
     if (rc) return rc;
     __half *dx = nullptr, *dy = nullptr;
-    const int out_c = (cout == 3) ? 4 : cout;
+    int out_c = (cout == 3) ? 4 : cout;
+    if (std::getenv("VR_BENCH_CSTRIDE") && cout != 3) out_c = cin_pad;
     VR_CUDA_CHECK(cudaMalloc(&dx, px * cin_pad * sizeof(__half)), dev.err);
     VR_CUDA_CHECK(cudaMalloc(&dy, px * out_c * sizeof(__half)), dev.err);
     VR_CUDA_CHECK(cudaMemset(dx, 0x11, px * cin_pad * sizeof(__half)), dev.err);  // small finite fp16 values
@@ -212,6 +227,14 @@ extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t ci
     c.act = ACT_LRELU;
     c.out = dy;
     c.out_cstride = out_c;
+    if (std::getenv("VR_BENCH_PLANAR") && cout != 3) {
+        // same bytes, chunk-planar: cin_pad / 32 source planes, destination plane(s) in a separate tensor
+        c.in_cstride = 32;
+        c.in_planes = cin_pad / 32;
+        c.in_pstride = static_cast<long long>(px) * 32;
+        c.out_cstride = 32;
+        c.out_pstride = static_cast<long long>(px) * 32;
+    }
     c.out_mode = (cout == 3) ? OUT_RGB4 : OUT_NHWC;
     c.rows = rows;
     c.flags = flags;

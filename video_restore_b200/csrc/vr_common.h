@@ -39,7 +39,9 @@ struct ConvWeights {
 
 struct ConvCall {
     const __half* in = nullptr;  // NHWC fp16
-    int in_cstride = 0;          // channels per pixel of the source buffer
+    int in_cstride = 0;          // channels per pixel of the source buffer (per plane); 32 = chunk-planar (ConvArgs)
+    int in_planes = 1;           // planes of the source tensor and their distance in elements (chunk-planar only)
+    long long in_pstride = 0;
     int cin_off = 0;
     int H = 0, W = 0;
     int y_begin = 0, y_end = -1;  // output row range (default: all rows)
@@ -48,6 +50,7 @@ struct ConvCall {
     float slope = 0.2f;
     __half* out = nullptr;
     int out_cstride = 0, out_coff = 0;
+    long long out_pstride = 0, res1_pstride = 0, res2_pstride = 0;  // plane distances (cstride == 32 tensors)
     const __half* res1 = nullptr;
     int res1_cstride = 0, res1_coff = 0;
     float s1 = 1.f;
@@ -95,10 +98,11 @@ struct Device {
     // Default 24 + 7: K3 wherever it fits, else K2, else K1. Measured in-network (720p x4plus, interleaved A/B, sustained clocks):
     // K1 only 42.7 ms, K2 on 32-channel layers 41.1 ms, K3 on 64-channel layers + K2 39.0 ms, K3 on both 36.9 ms.
     int rolling = 31;
+    bool planar = true;   // VR_PLANAR=0: interleaved [pixel][C] activation tensors instead of chunk-planar ones (A/B)
     int max_ctas = 0;     // test hook (VR_MAX_CTAS): cap K2 / K3 grids so that a CTA / CTA pair walks several work items
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
-    // tensor-map cache: (ptr, cstride, W, H, rows, kc)
-    std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> tmaps;
+    // tensor-map cache: (ptr, cstride, W, H, rows, kc, planes, pstride)
+    std::map<std::tuple<const void*, int, int, int, int, int, int, long long>, CUtensorMap> tmaps;
 };
 
 int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const float* prelu, int cin, int cout,
