@@ -190,7 +190,8 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
         if (x_base + px < a.W) {
             const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
             const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
-            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride) = val;
+            if (a.l2_hint) ptx::stg128_hint(orow + static_cast<size_t>(px) * a.omul * a.out_cstride, val, ptx::l2_policy_evict_last());
+            else *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride) = val;
         }
     }
     __syncwarp();
@@ -285,6 +286,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
         // ===================== TMA producer: this CTA's strip; bytes counted on the leader's barrier =====================
         if (lane == 0) {
             const uint32_t lead_full = ptx::map_to_rank(&full[0], 0);
+            const uint64_t pol_keep = ptx::l2_policy_evict_last(), pol_stream = ptx::l2_policy_evict_first();
             int s = 0;
             uint32_t ph = 0;
             for (int item = cluster_id; item < num_items; item += nclusters) {
@@ -297,8 +299,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                         ptx::mbar_wait(&empty[s], ph ^ 1);
                         if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
                         const int ch0 = a.cin_off + c * T::KC;
-                        ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0, sx * 128 - 1,
-                                              y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0);
+                        if (a.l2_hint)
+                            ptx::tma_load_4d_pair_hint(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0,
+                                                       sx * 128 - 1, y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0,
+                                                       c == nch - 1 ? pol_keep : pol_stream);
+                        else
+                            ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0,
+                                                  sx * 128 - 1, y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0);
                         if (++s == nslots) { s = 0; ph ^= 1; }
                     }
                 }

@@ -95,6 +95,7 @@ struct ConvArgs {
     int band, nbands;
     int nsplit;  // 1, or 2: the layer's 2N output channels are computed as two independent N-channel halves
     int unit;    // K3: boxes per issuer hand-over
+    int l2_hint; // K3: 1 = newest source plane and the output evict_last, older source planes evict_first (VR_L2HINT)
     long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 

@@ -314,6 +314,13 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     a.wpack = w.wpair;
     a.nstages = nslots;
     {
+        static const int env_hint = []() {
+            const char* e = std::getenv("VR_L2HINT");
+            return e ? std::atoi(e) : 0;
+        }();
+        a.l2_hint = env_hint;
+    }
+    {
         // boxes per issuer hand-over: the next unit's operands should be landing while the current one executes
         static const int env_unit = []() {
             const char* e = std::getenv("VR_UNIT");

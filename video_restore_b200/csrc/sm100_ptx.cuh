@@ -325,5 +325,30 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                  : "memory");
 }
 
+// L2 cache-policy hints (createpolicy): evict_last keeps lines resident under streaming traffic, evict_first marks stream-once data
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_4d_pair_hint(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1,
+                                                      int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster_addr), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void stg128_hint(void* gptr, const uint4& v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+                 "l"(policy)
+                 : "memory");
+}
+
 }  // namespace ptx
 }  // namespace vr
