@@ -37,8 +37,8 @@ struct PairTraits {
     static constexpr int kBHalf = 3 * kBTap;                     // ... of one chunk: 9216 (N = 32) / 18432 (N = 64) bytes
     static constexpr int kPhys = 512 / N;                        // physical ring blocks in TMEM
     static constexpr int kPeriod = kPhys - 2;                    // logical ring period (two blocks are mirrors)
-    // 8 epilogue warps = two rows in flight. 16 warps (four rows, <= 107 registers, ~100 B of spills) were measured slower on every
-    // layer shape (e.g. 160 -> 32: 79.5 vs 67.6 us).
+    // 8 epilogue warps = two rows in flight. More were measured slower on every layer shape: 16 warps (96 registers, ~100 B of
+    // spills) 160 -> 32 79.5 vs 67.6 us; 12 warps (128 registers) 64 -> 32 36.9 vs 35.3 us.
     static constexpr int kEpi = 8;                               // epilogue warps
     static constexpr int kGroups = kEpi / 4;                     // rows in flight
     static constexpr int kThreads = (kEpi + 1 + kMmaWarps) * 32;
@@ -264,7 +264,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             float bz[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) bz[j] = s_bias[g * 32 + j];
-            for (uint32_t blk = (warp >> 2) * (T::kPhys / T::kGroups); blk < (static_cast<uint32_t>(warp >> 2) + 1) * (T::kPhys / T::kGroups); ++blk) {
+            for (uint32_t blk = warp >> 2; blk < static_cast<uint32_t>(T::kPhys); blk += T::kGroups) {
                 if (blk < P) ptx::tmem_st32(tmem_base + lane_base + blk * N + g * 32, bz);
                 else ptx::tmem_st32_zero(tmem_base + lane_base + blk * N + g * 32);
             }
@@ -409,7 +409,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             bool xgap = false;
             for (int j = 0; j < a.ngx; ++j) xgap |= ((x >> a.gshift) == a.gx[j]);
 #pragma unroll 1
-            for (int l = static_cast<int>((rgrp - g0) & (T::kGroups - 1)); l < lrows; l += T::kGroups) {
+            for (int l = static_cast<int>((rgrp + T::kGroups - g0 % T::kGroups) % T::kGroups); l < lrows; l += T::kGroups) {
                 const uint32_t gl = g0 + l;
                 const uint32_t m = gl % P;
                 ptx::mbar_wait(&tfull[m], (gl / P) & 1u);
