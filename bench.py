@@ -319,6 +319,14 @@ def main():
     fps = world * K / (dev_ms / 1e3)
     e2e_fps = world * K / (e2e_ms / 1e3)
     conv_tflops = executed / (conv_ms_1 / 1e3) / 1e12
+    hbm_side = None
+    if k1_traffic.get("dram_bytes_per_launch") and wl["model"] == "RealESRGAN_x4plus":
+        # the ncu capture is the 720p single-tile x4plus frame: bytes scale with the pixels the launches process
+        from video_restore_b200.models import flops_per_input_pixel
+        scale = executed / (flops_per_input_pixel(MODEL_ZOO[wl["model"]]) * 720 * 1280)
+        gbs = k1_traffic["dram_bytes_per_launch"] * scale * n_conv_launches / (conv_ms_1 / 1e3) / 1e9
+        hbm_side = {"achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                    "note": "DRAM bytes per launch from the ncu capture (720p single tile) x pixel ratio x launches / conv time"}
     line = {
         "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -336,6 +344,9 @@ def main():
                      "algorithmic_flop_per_launch": executed / max(n_conv_launches, 1),
                      "avg_launch_us": conv_ms_1 * 1e3 / max(n_conv_launches, 1),
                      "conv_ms_per_step": conv_ms_1, "step_ms": total_ms_1,
+                     # second roofline of the same launches: DRAM bytes (ncu, per launch) x launches / conv time against the measured
+                     # copy bandwidth -- the 32-channel layers of K3 sit on this one
+                     "hbm": hbm_side,
                      "useful_tflops_whole_step": useful / (dev_ms / K / 1e3) / 1e12,
                      "useful_frac_of_sustained": useful / (dev_ms / K / 1e3) / 1e12 / peaks["sustained"]},
         "boundary_exchange_ms": boundary_ms,
