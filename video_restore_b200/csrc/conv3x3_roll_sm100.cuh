@@ -12,12 +12,13 @@
 //     per (chunk, dx, k16) -- full N on every row except the first / last two of the band (band ~ 50..100 rows);
 //   * accumulators are a RING of 512 / Cout output rows in TMEM. Output row r is first touched by input row r-1 and
 //     complete after input row r+1; the epilogue drains it while the MMAs run 2..R-3 rows ahead and hands the block back
-//     ZEROED (tcgen05.st), so every MMA accumulates and the issue sequence has no special first step;
+//     re-initialised with the BIAS row (tcgen05.st), so every MMA accumulates and the issue sequence has no special first step;
 //   * the whole layer's weights (up to 110 KB) stay resident in shared memory for the CTA's lifetime; a 192 -> 64 layer
 //     (221 KB) is computed as two independent 32-channel halves (work items x2, each half resident).
-// Shared memory: [weights nchunks x 9 N x 64 B][ring of <= 16 activation slots, 130 px x 64 B each][epilogue staging].
+// Shared memory: [weights nchunks x 9 N x 64 B][ring of <= 8 activation slots, 2 rows x 130 px x 64 B each][epilogue staging].
 // Warp roles as in K1: 0..7 epilogue (warp % 4 = TMEM lane quarter, warp / 4 = row parity), 8 = TMA producer, 9 / 10 =
-// MMA issuers alternating slots. Same operand layouts, descriptors and epilogue (epi_row_nhwc) as K1.
+// MMA issuers alternating slots. Same operand layouts and descriptors as K1; epilogue epi_row_nhwc_folded (bias lives in the
+// accumulators). Since K3 (conv3x3_pair_sm100.cuh) this kernel is the fall-back and the A/B baseline.
 #pragma once
 #include "conv3x3_sm100.cuh"
 

@@ -92,7 +92,7 @@ struct Device {
     bool multi_layer = false;
     bool fold_upsample = true;     // VR_FOLD_UP=0: materialise nearest x2 and run conv_up1/2 as plain 3x3 convs
     bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
-    // VR_ROLL bit mask: which NHWC 3x3 layers run on the rolling-row kernel K2 instead of the tiled kernel K1:
+    // VR_ROLL bit mask: which NHWC 3x3 layers run on the rolling-row kernels K2 / K3 instead of the tiled kernel K1:
     // 1 = 32-channel outputs, 2 = 64-channel outputs whose weights fit (cin <= 128), 4 = 64-channel outputs as two halves;
     // 8 / 16 = 32- / 64-channel outputs on the CTA-pair kernel K3 (takes precedence)
     // Default 24 + 7: K3 wherever it fits, else K2, else K1. Measured in-network (720p x4plus, interleaved A/B, sustained clocks):
