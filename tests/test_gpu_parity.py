@@ -118,6 +118,22 @@ def test_conv_chunk_planar_tensors(gpu_lib, kernel):
         _conv_case(gpu_lib, 12, 140, 64, 48, flags=fl)     # pixel shuffle + base
 
 
+@pytest.mark.parametrize("kernel", [FORCE_ROLL, FORCE_PAIR])
+def test_conv_rolling_random_shapes(gpu_lib, kernel):
+    """Seeded random layer shapes / epilogues / layouts: band and strip edges, ring phases and mirror positions land differently
+    for every (H, W); channel counts are the ones the model zoo produces."""
+    rng = np.random.default_rng(20261018)
+    for i in range(14):
+        cout = int(rng.choice([32, 64]))
+        cin = int(rng.choice([3, 12, 32, 64, 96, 128, 160, 192] if cout == 64 else [32, 64, 96, 128, 160]))
+        H, W = int(rng.integers(1, 90)), int(rng.integers(1, 420))
+        kw = dict(act=int(rng.integers(0, 2)), res=int(rng.integers(0, 3)), seed=100 + i)
+        if rng.random() < 0.25:
+            kw = dict(prelu=True, res=kw["res"], seed=100 + i)
+        fl = kernel + (PLANAR if rng.random() < 0.5 else 0)
+        _conv_case(gpu_lib, H, W, cin, cout, flags=fl, **kw)
+
+
 @pytest.mark.parametrize("flags", [FORCE_ROLL, FORCE_PAIR])
 def test_conv_rolling_several_items_per_cta(gpu_lib, monkeypatch, flags):
     """Grid capped at 6 CTAs (3 pairs): every CTA / pair walks several (band, strip) items, so the TMEM ring, the slot ring and
