@@ -592,6 +592,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     if (const char* e = std::getenv("VR_PDL")) h->dev.use_pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_ROLL")) h->dev.rolling = std::atoi(e);
     if (const char* e = std::getenv("VR_PLANAR")) h->dev.planar = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_PAIRPAD")) h->dev.pair_pad = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_WRES")) h->dev.weights_resident = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;

@@ -1,6 +1,6 @@
 // K3: paired rolling-row 3x3 convolution -- K2 (conv3x3_roll_sm100.cuh) on CTA PAIRS with tcgen05 cta_group::2.
 //
-// A cluster of two CTAs (two SMs of one TPC) owns two adjacent 128-pixel strips of one band of rows. The leader (cluster
+// A cluster of two CTAs (two SMs of one TPC) owns two 128-pixel strips x bands of rows (normally neighbours). The leader (cluster
 // rank 0) issues every MMA with M = 256: each CTA supplies the activations of ITS strip (A) and HALF of the weight rows (B)
 // at the same shared-memory offsets, and finds its strip's accumulators in its own TMEM (tools/mma2cta_probe). Per SM an
 // MMA therefore reads 4 KB of A but only half of B:
@@ -197,6 +197,33 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
     __syncwarp();
 }
 
+// Work decomposition: sub-items u = band * tiles_x + strip (strip fastest); cluster item i = sub-items 2i (rank 0) and 2i+1
+// (rank 1). The two CTAs of a pair only have to run the same NUMBER of rows -- the leader's MMA sequence is shared, the image
+// rows / strip each CTA loads and stores are its own -- so an odd strip count costs no padding strip (the tile atlas of the
+// 6-tile preset is 13 strips wide). A CTA whose band is shorter than its peer's just runs extra discarded rows; a sub-item
+// past the end is empty (strip beyond the image: zero-filled loads, no stores).
+struct PairSub {
+    int sx, y0, nrow;
+};
+__device__ __forceinline__ PairSub pair_sub(const ConvArgs& a, int u) {
+    PairSub r;
+    if (u >= a.tiles_x * a.nbands) {
+        r.sx = a.tiles_x;
+        r.y0 = a.y_begin;
+        r.nrow = 0;
+        return r;
+    }
+    const int b = u / a.tiles_x;
+    r.sx = u - b * a.tiles_x;
+    r.y0 = a.y_begin + b * a.band;
+    r.nrow = (r.y0 + a.band < a.y_end ? r.y0 + a.band : a.y_end) - r.y0;
+    return r;
+}
+__device__ __forceinline__ int pair_rows(const ConvArgs& a, int item) {  // rows the pair runs: the longer of the two bands
+    const int n0 = pair_sub(a, 2 * item).nrow, n1 = pair_sub(a, 2 * item + 1).nrow;
+    return n0 > n1 ? n0 : n1;
+}
+
 template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairTraits<N>::kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
@@ -278,8 +305,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    const int pairs_x = (a.tiles_x + 1) >> 1;
-    const int num_items = pairs_x * a.nbands;
+    const int num_items = (a.tiles_x * a.nbands + 1) >> 1;
     const int cluster_id = static_cast<int>(blockIdx.x) >> 1, nclusters = static_cast<int>(gridDim.x) >> 1;
 
     if (warp == T::kEpi) {
@@ -290,10 +316,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             int s = 0;
             uint32_t ph = 0;
             for (int item = cluster_id; item < num_items; item += nclusters) {
-                const int b = item / pairs_x, sx = (item - b * pairs_x) * 2 + static_cast<int>(rank);
-                const int y0 = a.y_begin + b * a.band;
-                const int nrow = (y0 + a.band < a.y_end ? y0 + a.band : a.y_end) - y0;
-                const int nin2 = (nrow + 3) & ~1;
+                const PairSub me = pair_sub(a, 2 * item + static_cast<int>(rank));
+                const int sx = me.sx, y0 = me.y0;
+                const int nin2 = (pair_rows(a, item) + 3) & ~1;
                 for (int j0 = 0; j0 < nin2; j0 += 2) {
                     for (int c = 0; c < nch; ++c) {
                         ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -326,10 +351,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
             int gunit = 0;
             uint32_t g0 = 0;  // logical rows started before the current item
             for (int item = cluster_id; item < num_items; item += nclusters) {
-                const int b = item / pairs_x;
-                const int y0 = a.y_begin + b * a.band;
-                const int nrow = (y0 + a.band < a.y_end ? y0 + a.band : a.y_end) - y0;
-                const int nin2 = (nrow + 3) & ~1;
+                const int nin2 = (pair_rows(a, item) + 3) & ~1;
                 const int nb = (nin2 >> 1) * nch;  // boxes of the item: row pairs x chunks, chunk fastest
                 int j0 = 0, c = 0;
                 for (int n = 0; n < nb; n += unit, ++gunit) {
@@ -399,10 +421,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
         const uint32_t lead_tempty = ptx::map_to_rank(&tempty[0], 0);
         uint32_t g0 = 0;
         for (int item = cluster_id; item < num_items; item += nclusters) {
-            const int b = item / pairs_x, sx = (item - b * pairs_x) * 2 + static_cast<int>(rank);
-            const int y0 = a.y_begin + b * a.band;
-            const int nrow = (y0 + a.band < a.y_end ? y0 + a.band : a.y_end) - y0;
-            const int nin2 = (nrow + 3) & ~1;
+            const PairSub me = pair_sub(a, 2 * item + static_cast<int>(rank));
+            const int sx = me.sx, y0 = me.y0, nrow = me.nrow;  // this CTA's own strip / band: real rows are l in [2, nrow + 2)
+            const int nin2 = (pair_rows(a, item) + 3) & ~1;
             const int lrows = nin2 + 2;
             const int x_base = sx * 128 + quarter * 32;
             const int x = x_base + lane;

@@ -335,10 +335,11 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
         a.unit = u < 1 ? 1 : u;
     }
     a.tiles_x = (a.W + 127) / 128;
-    const int pairs_x = (a.tiles_x + 1) / 2;
     const int max_clusters = dev.sm_count / 2;
-    choose_bands(pairs_x, a.y_end - a.y_begin, max_clusters, &a.band, &a.nbands);
-    const int items = pairs_x * a.nbands;
+    if (dev.pair_pad) a.tiles_x = (a.tiles_x + 1) & ~1;  // A/B: pairs of adjacent strips with a padding strip
+    // sub-items = strips x bands, two per cluster (any two with consecutive indices: no padding strip for odd strip counts)
+    choose_bands(a.tiles_x, a.y_end - a.y_begin, 2 * max_clusters, &a.band, &a.nbands);
+    const int items = (a.tiles_x * a.nbands + 1) / 2;
     int nclusters = items < max_clusters ? items : max_clusters;
     if (dev.max_ctas > 1 && nclusters > dev.max_ctas / 2) nclusters = dev.max_ctas / 2;
     cudaLaunchConfig_t cfg = {};

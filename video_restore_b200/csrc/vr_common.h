@@ -99,6 +99,7 @@ struct Device {
     // K1 only 42.7 ms, K2 on 32-channel layers 41.1 ms, K3 on 64-channel layers + K2 39.0 ms, K3 on both 36.9 ms.
     int rolling = 31;
     bool planar = true;   // VR_PLANAR=0: interleaved [pixel][C] activation tensors instead of chunk-planar ones (A/B)
+    bool pair_pad = false;  // VR_PAIRPAD=1: K3 pairs adjacent strips only (odd strip counts get a padding strip), for A/B runs
     int max_ctas = 0;     // test hook (VR_MAX_CTAS): cap K2 / K3 grids so that a CTA / CTA pair walks several work items
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
     // tensor-map cache: (ptr, cstride, W, H, rows, kc, planes, pstride)
