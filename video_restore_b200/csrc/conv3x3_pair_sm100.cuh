@@ -190,7 +190,7 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
         if (x_base + px < a.W) {
             const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
             const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
-            if (a.l2_hint) ptx::stg128_hint(orow + static_cast<size_t>(px) * a.omul * a.out_cstride, val, ptx::l2_policy_evict_last());
+            if (a.l2_hint == 1) ptx::stg128_hint(orow + static_cast<size_t>(px) * a.omul * a.out_cstride, val, ptx::l2_policy_evict_last());
             else *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride) = val;
         }
     }
@@ -327,7 +327,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                         if (a.l2_hint)
                             ptx::tma_load_4d_pair_hint(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0,
                                                        sx * 128 - 1, y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0,
-                                                       c == nch - 1 ? pol_keep : pol_stream);
+                                                       (a.l2_hint == 1 ? c == nch - 1 : c < a.l2_hint - 1) ? pol_keep : pol_stream);
                         else
                             ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0,
                                                   sx * 128 - 1, y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0);

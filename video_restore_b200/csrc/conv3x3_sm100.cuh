@@ -95,7 +95,8 @@ struct ConvArgs {
     int band, nbands;
     int nsplit;  // 1, or 2: the layer's 2N output channels are computed as two independent N-channel halves
     int unit;    // K3: boxes per issuer hand-over
-    int l2_hint; // K3: 1 = newest source plane and the output evict_last, older source planes evict_first (VR_L2HINT)
+    int l2_hint; // K3 (VR_L2HINT): 1 = newest source plane and the output evict_last, older source planes evict_first;
+                 // 2 / 3 = the first one / two source planes (the dense block's x) evict_last, everything else streams
     long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 
