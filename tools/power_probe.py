@@ -6,7 +6,7 @@ import pynvml
 from video_restore_b200 import _lib
 pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
 names = {0: "full", 2: "skip-tma", 4: "skip-mma", 8: "skip-epi", 10: "mma-only", 12: "tma-only", 6: "epi-only",
-         512: "K3 full", 516: "K3 skip-mma", 520: "K3 skip-epi", 64: "K1 full"}
+         512: "K3 full", 516: "K3 skip-mma", 520: "K3 skip-epi", 528: "K3 no-stores", 64: "K1 full"}
 def run(cin, cout, fl, iters, rows=4, H=720):
     samples = []; stop = threading.Event()
     def samp():
@@ -31,6 +31,12 @@ elif mode == "k3":
         for fl, rows in ((64, 4), (512, 0), (516, 0), (520, 0)):
             base = _lib.conv3x3_bench(720, 1280, cin, cout, rows=rows, flags=fl, iters=5)
             run(cin, cout, fl, max(50, int(2000.0 / base)), rows)
+elif mode == "epi":
+    # what in the epilogue costs power: full / without the global stores / without the whole epilogue
+    for cin, cout in [(192, 64), (160, 32), (64, 64)]:
+        for fl in (512, 528, 520):
+            base = _lib.conv3x3_bench(720, 1280, cin, cout, rows=0, flags=fl, iters=5)
+            run(cin, cout, fl, max(50, int(3000.0 / base)), 0)
 elif mode == "l2":
     # same layer on an image whose source + destination fit the 126 MB L2 (re-read from L2 every iteration) and on 720 rows
     for cin, cout in [(128, 32), (64, 32)]:

@@ -190,6 +190,7 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
         if (x_base + px < a.W) {
             const int swz_r = kVec == 8 ? (px & 7) : ((px >> 1) & 3);
             const uint4 val = ptx::lds128(stg_s + px * kStgPitch + ((un ^ swz_r) << 4));
+            if (a.flags & FLAG_SKIP_B) continue;  // ablation (power probe): everything but the global stores
             if (a.l2_hint == 1) ptx::stg128_hint(orow + static_cast<size_t>(px) * a.omul * a.out_cstride, val, ptx::l2_policy_evict_last());
             else *reinterpret_cast<uint4*>(orow + static_cast<size_t>(px) * a.omul * a.out_cstride) = val;
         }
