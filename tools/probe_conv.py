@@ -158,6 +158,12 @@ def main():
                 except Exception as e:  # noqa: BLE001
                     print(f"[rbench] {cin}->{cout} {label}: ERROR {e}", flush=True)
                     return
+    elif group == "e64":
+        # 64-channel K3 layers under the current VR_EARLY64 setting (conv3x3_bench layers have no residual operands)
+        for H, W in ((720, 1280), (480, 854)):
+            for cin, cout in [(64, 64), (128, 64), (192, 64)]:
+                ms = _lib.conv3x3_bench(H, W, cin, cout, rows=0, flags=512, iters=30)
+                print(f"[e64] {H}x{W} {cin}->{cout} K3: {ms*1e3:8.1f} us  {2.0*H*W*cin*cout*9/ms/1e9:7.1f} TFLOP/s", flush=True)
     elif group == "one":
         cin, cout = int(sys.argv[2]), int(sys.argv[3])
         fl = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 0

@@ -2,12 +2,14 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libvrb200.so"
+# VR_LIB: another build of the same library (A/B runs of kernel changes on one box); default the in-tree build
+LIB_PATH = Path(os.environ["VR_LIB"]) if os.environ.get("VR_LIB") else _PKG / "libvrb200.so"
 
 VR_MODEL_RRDBNET, VR_MODEL_SRVGG = 0, 1
 VR_BLEND_CROP, VR_BLEND_GAUSSIAN = 0, 1

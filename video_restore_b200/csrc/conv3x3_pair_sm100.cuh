@@ -84,101 +84,117 @@ __device__ __forceinline__ void pair_release(uint32_t t_main, uint32_t t_mir, co
     if (lane == 0) ptx::mbar_arrive_cluster(release_addr);
 }
 
-// One output row x 32 pixels of this warp's lane quarter: accumulators (bias included; + mirror block when t_mir != ~0u) ->
-// activation -> residuals -> fp16 -> swizzled staging -> coalesced stores. Per 32-channel group, like epi_row_nhwc.
+// activation of 32 accumulator values (amode: 0 none, 1 leaky with slope in [0, 1], 2 per-channel negative slope table)
+__device__ __forceinline__ void epi_act32(float* v, int amode, float slope, const float* neg) {
+    if (amode == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+    } else if (amode == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + neg[j] * fminf(v[j], 0.f);
+    }
+}
+// 32 channels of this lane's pixel -> fp16 -> the warp's swizzled staging buffer (16 B unit u of group g)
 template <int N>
-__device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main, uint32_t t_mir, uint32_t stg_s, int lane, int x_base,
+__device__ __forceinline__ void epi_stage32(const float* v, uint32_t stg_s, int lane, int g) {
+    constexpr int kVec = N / 8;
+    const int swz_w = kVec == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * (N * 2) + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
+}
+
+// One output row x 32 pixels of this warp's lane quarter: accumulators (bias included; + mirror block when t_mir != ~0u) ->
+// activation -> residuals -> fp16 -> swizzled staging -> coalesced stores. Returns true when the ring position has already
+// been handed back (otherwise the caller does it).
+template <int N>
+__device__ __forceinline__ bool epi_row_pair(const ConvArgs& a, uint32_t t_main, uint32_t t_mir, uint32_t stg_s, int lane, int x_base,
                                              int y, bool gap, const float* s_bias, const float* s_neg, int amode,
                                              uint32_t release_addr) {
     constexpr int kVec = N / 8;
     constexpr int kStgPitch = N * 2;
     const int x = x_base + lane;
     const bool inb = x < a.W;
-    const size_t p = static_cast<size_t>(y) * a.W + x;
     const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
-    uint4 q1[kVec], q2[kVec];
-    if (inb && has1) {
+    // The ring position is handed back as early as the registers allow -- a position held through the global stores keeps
+    // the issuers waiting (with N = 64 the ring has only six logical positions). N = 32: right after the TMEM loads (the
+    // whole row is 32 registers). N = 64: after the row is staged in shared memory, before the global stores (a.early64,
+    // VR_EARLY64=0 for A/B runs: by the caller after the stores). Loading all 64 columns first and releasing before the
+    // arithmetic was measured as well: 168 registers are not enough for it (spills), slower than this.
+    const bool early = N == 32 || a.early64 != 0;
+    {
+        const size_t p = static_cast<size_t>(y) * a.W + x;
+        uint4 q1[kVec], q2[kVec];
+        if (inb && has1) {
 #pragma unroll
-        for (int j = 0; j < kVec; ++j)
-            q1[j] = __ldg(reinterpret_cast<const uint4*>(a.res1 + chan_off(p, a.res1_cstride, a.res1_pstride, a.res1_coff + j * 8)));
-    }
-    if (inb && has2) {
-#pragma unroll
-        for (int j = 0; j < kVec; ++j)  // may alias `out` (in-place RRDB skip)
-            q2[j] = *reinterpret_cast<const uint4*>(a.res2 + chan_off(p, a.res2_cstride, a.res2_pstride, a.res2_coff + j * 8));
-    }
-    // N == 32: the whole row is loaded first and the ring position is handed back BEFORE the arithmetic and the stores (the
-    // remote arrive has cluster-scope release semantics: issued after the stores it would wait for them to drain).
-    // N == 64 (MMA-bound layers, twice the registers): per 32-channel group, position handed back by the caller afterwards.
-    constexpr bool kEarly = N == 32;
-    float v0[32];
-    if constexpr (kEarly) {
-        if (t_mir != 0xffffffffu) {
-            uint32_t r0[32], r1[32];
-            ptx::tmem_ld32_issue(t_main, r0);
-            ptx::tmem_ld32_issue(t_mir, r1);
-            ptx::tmem_ld32_wait(r0);
-            ptx::tmem_ld32_wait(r1);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v0[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
-        } else {
-            ptx::tmem_ld32(t_main, v0);
+            for (int j = 0; j < kVec; ++j)
+                q1[j] = __ldg(reinterpret_cast<const uint4*>(a.res1 + chan_off(p, a.res1_cstride, a.res1_pstride, a.res1_coff + j * 8)));
         }
-        pair_release<N>(t_main, t_mir, s_bias, lane, release_addr);
-    }
+        if (inb && has2) {
 #pragma unroll
-    for (int g = 0; g < N / 32; ++g) {
-        float v[32];
-        if constexpr (kEarly) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v0[j];
-        } else if (t_mir != 0xffffffffu) {
-            uint32_t r0[32], r1[32];
-            ptx::tmem_ld32_issue(t_main + g * 32, r0);
-            ptx::tmem_ld32_issue(t_mir + g * 32, r1);
-            ptx::tmem_ld32_wait(r0);
-            ptx::tmem_ld32_wait(r1);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
-        } else {
-            ptx::tmem_ld32(t_main + g * 32, v);
+            for (int j = 0; j < kVec; ++j)  // may alias `out` (in-place RRDB skip)
+                q2[j] = *reinterpret_cast<const uint4*>(a.res2 + chan_off(p, a.res2_cstride, a.res2_pstride, a.res2_coff + j * 8));
         }
-        if (inb) {
-            if (amode == 1) {
-                const float sl = a.slope;
+        float v0[32];
+        if constexpr (N == 32) {
+            if (t_mir != 0xffffffffu) {
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld32_issue(t_main, r0);
+                ptx::tmem_ld32_issue(t_mir, r1);
+                ptx::tmem_ld32_wait(r0);
+                ptx::tmem_ld32_wait(r1);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * sl);
-            } else if (amode == 2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + s_neg[g * 32 + j] * fminf(v[j], 0.f);
+                for (int j = 0; j < 32; ++j) v0[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+            } else {
+                ptx::tmem_ld32(t_main, v0);
             }
-            if (has1) {
+            pair_release<N>(t_main, t_mir, s_bias, lane, release_addr);
+        }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float f[8];
-                    unpack8(q1[g * 4 + u], f);
+        for (int g = 0; g < N / 32; ++g) {
+            float v[32];
+            if constexpr (N == 32) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
+                for (int j = 0; j < 32; ++j) v[j] = v0[j];
+            } else if (t_mir != 0xffffffffu) {
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld32_issue(t_main + g * 32, r0);
+                ptx::tmem_ld32_issue(t_mir + g * 32, r1);
+                ptx::tmem_ld32_wait(r0);
+                ptx::tmem_ld32_wait(r1);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+            } else {
+                ptx::tmem_ld32(t_main + g * 32, v);
+            }
+            if (inb) {
+                epi_act32(v, amode, a.slope, s_neg + g * 32);
+                if (has1) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float f[8];
+                        unpack8(q1[g * 4 + u], f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
+                    }
+                }
+                if (has2) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float f[8];
+                        unpack8(q2[g * 4 + u], f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
+                    }
                 }
             }
-            if (has2) {
+            if (gap) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float f[8];
-                    unpack8(q2[g * 4 + u], f);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
-                }
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
+            epi_stage32<N>(v, stg_s, lane, g);
         }
-        if (gap) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        const int swz_w = kVec == 8 ? (lane & 7) : ((lane >> 1) & 3);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * kStgPitch + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
     }
+    if (N == 64 && early) pair_release<N>(t_main, t_mir, s_bias, lane, release_addr);
     __syncwarp();
     // lane l always handles 16 B unit l % kVec of its pixels (32 % kVec == 0)
     __half* orow = a.out + chan_off(static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx, a.out_cstride,
@@ -196,6 +212,105 @@ __device__ __forceinline__ void epi_row_pair(const ConvArgs& a, uint32_t t_main,
         }
     }
     __syncwarp();
+    return early;  // ring position already handed back
+}
+
+// The same row without the staging transpose: a lane's 32 accumulator columns ARE 64 contiguous bytes of its pixel (one
+// channel group of a chunk-planar or 32-channel-multiple tensor), so it stores them itself with two 256-bit stores -- every
+// store fills whole 32-byte sectors, and the shared-memory traffic of the transpose (16 KB written + 16 KB read per row and
+// CTA at N = 64) is gone. That traffic matters: the MMAs alone read 5.5 KB (N = 32) / 7 KB (N = 64) of operands per 48 / 96
+// cycles from shared memory, 90 % / 57 % of its 128 B/cycle, and the TMA writes the activations on top.
+template <int N>
+__device__ __forceinline__ bool epi_row_pair_direct(const ConvArgs& a, uint32_t t_main, uint32_t t_mir, int lane, int x_base, int y, bool gap,
+                                                    const float* s_bias, const float* s_neg, int amode, uint32_t release_addr) {
+    constexpr int kG = N / 32;
+    const int x = x_base + lane;
+    const bool inb = x < a.W;
+    const size_t p = static_cast<size_t>(y) * a.W + x;
+    const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
+    uint4 q1[kG * 4], q2[kG * 4];
+    if (inb && has1) {
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+            const __half* r = a.res1 + chan_off(p, a.res1_cstride, a.res1_pstride, a.res1_coff + g * 32);
+            ptx::ldg256_nc(r, q1[g * 4], q1[g * 4 + 1]);
+            ptx::ldg256_nc(r + 16, q1[g * 4 + 2], q1[g * 4 + 3]);
+        }
+    }
+    if (inb && has2) {
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {  // may alias `out` (in-place RRDB skip): read and written by the same lane
+            const __half* r = a.res2 + chan_off(p, a.res2_cstride, a.res2_pstride, a.res2_coff + g * 32);
+            ptx::ldg256(r, q2[g * 4], q2[g * 4 + 1]);
+            ptx::ldg256(r + 16, q2[g * 4 + 2], q2[g * 4 + 3]);
+        }
+    }
+    float v0[32];
+    if constexpr (N == 32) {
+        if (t_mir != 0xffffffffu) {
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld32_issue(t_main, r0);
+            ptx::tmem_ld32_issue(t_mir, r1);
+            ptx::tmem_ld32_wait(r0);
+            ptx::tmem_ld32_wait(r1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v0[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        } else {
+            ptx::tmem_ld32(t_main, v0);
+        }
+        pair_release<N>(t_main, t_mir, s_bias, lane, release_addr);
+    }
+    const bool store = inb && !(a.flags & FLAG_SKIP_B);
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+        float v[32];
+        if constexpr (N == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v0[j];
+        } else if (t_mir != 0xffffffffu) {
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld32_issue(t_main + g * 32, r0);
+            ptx::tmem_ld32_issue(t_mir + g * 32, r1);
+            ptx::tmem_ld32_wait(r0);
+            ptx::tmem_ld32_wait(r1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        } else {
+            ptx::tmem_ld32(t_main + g * 32, v);
+        }
+        epi_act32(v, amode, a.slope, s_neg + g * 32);
+        if (has1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(q1[g * 4 + u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s1, f[j]);
+            }
+        }
+        if (has2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(q2[g * 4 + u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u * 8 + j] = fmaf(v[u * 8 + j], a.s2, f[j]);
+            }
+        }
+        if (gap) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        const uint4 h0 = pack8(v), h1 = pack8(v + 8), h2 = pack8(v + 16), h3 = pack8(v + 24);
+        // N = 64: all TMEM reads are done after the last group; the position goes back while only the packed row is live
+        if (N == 64 && g == kG - 1) pair_release<N>(t_main, t_mir, s_bias, lane, release_addr);
+        if (store) {
+            __half* o = a.out + chan_off(p, a.out_cstride, a.out_pstride, a.out_coff + g * 32);
+            ptx::stg256(o, h0, h1);
+            ptx::stg256(o + 16, h2, h3);
+        }
+    }
+    return true;
 }
 
 // Work decomposition: sub-items u = band * tiles_x + strip (strip fastest); cluster item i = sub-items 2i (rank 0) and 2i+1
@@ -225,7 +340,7 @@ __device__ __forceinline__ int pair_rows(const ConvArgs& a, int item) {  // rows
     return n0 > n1 ? n0 : n1;
 }
 
-template <int N>
+template <int N, bool kDirect>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairTraits<N>::kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     using T = PairTraits<N>;
@@ -439,13 +554,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                 const uint32_t t_main = tmem_base + lane_base + m * N;
                 const uint32_t t_mir = m < 2 ? tmem_base + lane_base + (P + m) * N : 0xffffffffu;
                 const bool real = l >= 2 && l < nrow + 2 && !(a.flags & FLAG_SKIP_EPI);
+                bool released = false;
                 if (real) {
                     const int y = y0 + l - 2;
                     bool gap = xgap;
                     for (int j = 0; j < a.ngy; ++j) gap |= ((y >> a.gshift) == a.gy[j]);
-                    epi_row_pair<N>(a, t_main, t_mir, stg_s, lane, x_base, y, gap, s_bias, s_neg, amode, lead_tempty + m * 8);
+                    if constexpr (kDirect) released = epi_row_pair_direct<N>(a, t_main, t_mir, lane, x_base, y, gap, s_bias, s_neg, amode, lead_tempty + m * 8);
+                    else released = epi_row_pair<N>(a, t_main, t_mir, stg_s, lane, x_base, y, gap, s_bias, s_neg, amode, lead_tempty + m * 8);
                 }
-                if (!real || N != 32) pair_release<N>(t_main, t_mir, s_bias, lane, lead_tempty + m * 8);
+                if (!released) pair_release<N>(t_main, t_mir, s_bias, lane, lead_tempty + m * 8);
             }
             g0 += lrows;
         }

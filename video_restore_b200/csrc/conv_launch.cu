@@ -300,15 +300,28 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     using T = PairTraits<N>;
     if (!w.wpair || w.cout != N) return 1;
     const int w_bytes = w.nchunks * T::kBHalf;
-    int nslots = (T::kBudget - w_bytes) / T::kASlot;
+    {
+        static const int env_direct = []() {
+            const char* e = std::getenv("VR_EPI_DIRECT");
+            return e ? std::atoi(e) : 1;
+        }();
+        // the direct epilogue needs 32-byte aligned 64-byte channel groups per pixel: chunk-planar tensors, or interleaved ones
+        // with 32-channel multiples
+        a.epi_direct = env_direct && a.omul == 1 && a.out_cstride % 32 == 0 && a.out_coff % 32 == 0 &&
+                       (!a.res1 || (a.res1_cstride % 32 == 0 && a.res1_coff % 32 == 0)) &&
+                       (!a.res2 || (a.res2_cstride % 32 == 0 && a.res2_coff % 32 == 0));
+    }
+    // the direct epilogue has no staging buffer: its shared memory goes to activation slots
+    const int stg_bytes = a.epi_direct ? 0 : T::kStgBytes;
+    int nslots = (T::kBudget + T::kStgBytes - stg_bytes - w_bytes) / T::kASlot;
     if (nslots < T::kMinSlots) return 1;
     if (nslots > kPairMaxSlots) nslots = kPairMaxSlots;
-    auto kern = conv3x3_pair_kernel<N>;
-    static bool attr_done[64] = {};
-    if (!attr_done[dev.ordinal & 63]) {
+    auto kern = a.epi_direct ? conv3x3_pair_kernel<N, true> : conv3x3_pair_kernel<N, false>;
+    static bool attr_done[2][64] = {};
+    if (!attr_done[a.epi_direct][dev.ordinal & 63]) {
         VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kBudget + T::kStgBytes + 1024),
                       dev.err);
-        attr_done[dev.ordinal & 63] = true;
+        attr_done[a.epi_direct][dev.ordinal & 63] = true;
     }
     a.nsplit = 1;
     a.wpack = w.wpair;
@@ -319,6 +332,11 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
             return e ? std::atoi(e) : 0;
         }();
         a.l2_hint = env_hint;
+        static const int env_early = []() {
+            const char* e = std::getenv("VR_EARLY64");
+            return e ? std::atoi(e) : 1;
+        }();
+        a.early64 = env_early;
     }
     {
         // boxes per issuer hand-over: the next unit's operands should be landing while the current one executes
@@ -345,7 +363,7 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * nclusters);  // the kernel is compiled with __cluster_dims__(2, 1, 1)
     cfg.blockDim = dim3(T::kThreads);
-    cfg.dynamicSmemBytes = w_bytes + nslots * T::kASlot + T::kStgBytes + 1024;
+    cfg.dynamicSmemBytes = w_bytes + nslots * T::kASlot + stg_bytes + 1024;
     cfg.stream = dev.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -350,5 +350,23 @@ __device__ __forceinline__ void stg128_hint(void* gptr, const uint4& v, uint64_t
                  : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.256): one lane moves a full 32-byte sector
+__device__ __forceinline__ void stg256(void* gptr, const uint4& lo, const uint4& hi) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+                 "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* gptr, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(gptr)
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(const void* gptr, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(gptr));
+}
+
 }  // namespace ptx
 }  // namespace vr
