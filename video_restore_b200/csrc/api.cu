@@ -3,6 +3,7 @@
 // Interface being replaced: reference video_upscaler.py:328-338 (constructor) and :490-505 (_process_frame).
 #include "../../include/vrb200.h"
 #include "conv3x3_sm100.cuh"
+#include <cstdio>
 #include "vr_common.h"
 
 #include <algorithm>
@@ -589,6 +590,15 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     h->dev.ordinal = cfg->device;
     h->dev.sm_count = p.multiProcessorCount;
     h->dev.err = &h->err;
+    if (const char* e = std::getenv("VR_L2PERSIST")) {
+        // experiment: L2 set-aside for evict_last / persisting lines, in MB (0 = leave the driver default); see VR_L2HINT
+        int max_persist = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
+        size_t want = static_cast<size_t>(std::atoi(e)) << 20;
+        if (want > static_cast<size_t>(max_persist)) want = static_cast<size_t>(max_persist);
+        cudaError_t pe = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        std::fprintf(stderr, "[vrb200] VR_L2PERSIST: max %d MB, set %zu MB (%s)\n", max_persist >> 20, want >> 20, cudaGetErrorString(pe));
+    }
     if (const char* e = std::getenv("VR_PDL")) h->dev.use_pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_ROLL")) h->dev.rolling = std::atoi(e);
     if (const char* e = std::getenv("VR_PLANAR")) h->dev.planar = std::atoi(e) != 0;

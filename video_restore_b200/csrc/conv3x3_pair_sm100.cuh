@@ -306,8 +306,14 @@ __device__ __forceinline__ bool epi_row_pair_direct(const ConvArgs& a, uint32_t 
         if (N == 64 && g == kG - 1) pair_release<N>(t_main, t_mir, s_bias, lane, release_addr);
         if (store) {
             __half* o = a.out + chan_off(p, a.out_cstride, a.out_pstride, a.out_coff + g * 32);
-            ptx::stg256(o, h0, h1);
-            ptx::stg256(o + 16, h2, h3);
+            if (N == 64 && a.l2_hint >= 4) {  // a 64-channel output is the next layers' x: same keep-fraction policy as their loads
+                const uint64_t pol = ptx::l2_policy_keep_fraction(a.l2_frac);
+                ptx::stg256_hint(o, h0, h1, pol);
+                ptx::stg256_hint(o + 16, h2, h3, pol);
+            } else {
+                ptx::stg256(o, h0, h1);
+                ptx::stg256(o + 16, h2, h3);
+            }
         }
     }
     return true;
@@ -428,7 +434,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
         // ===================== TMA producer: this CTA's strip; bytes counted on the leader's barrier =====================
         if (lane == 0) {
             const uint32_t lead_full = ptx::map_to_rank(&full[0], 0);
-            const uint64_t pol_keep = ptx::l2_policy_evict_last(), pol_stream = ptx::l2_policy_evict_first();
+            const uint64_t pol_keep = a.l2_hint >= 4 ? ptx::l2_policy_keep_fraction(a.l2_frac) : ptx::l2_policy_evict_last();
+            const uint64_t pol_stream = ptx::l2_policy_evict_first();
+            // chunks (source planes) below keep_end use pol_keep; l2_hint == 1 keeps the newest plane only
+            const int keep_end = a.l2_hint == 1 ? nch : a.l2_hint <= 3 ? a.l2_hint - 1 : a.l2_hint == 4 ? 2 : a.l2_hint == 5 ? 3 : nch;
+            const int keep_begin = a.l2_hint == 1 ? nch - 1 : 0;
             int s = 0;
             uint32_t ph = 0;
             for (int item = cluster_id; item < num_items; item += nclusters) {
@@ -443,7 +453,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                         if (a.l2_hint)
                             ptx::tma_load_4d_pair_hint(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0,
                                                        sx * 128 - 1, y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0,
-                                                       (a.l2_hint == 1 ? c == nch - 1 : c < a.l2_hint - 1) ? pol_keep : pol_stream);
+                                                       (c >= keep_begin && c < keep_end) ? pol_keep : pol_stream);
                         else
                             ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0,
                                                   sx * 128 - 1, y0 - 1 + j0, a.in_cstride == 32 ? ch0 >> 5 : 0);

@@ -98,7 +98,10 @@ struct ConvArgs {
     int early64; // K3, 64 output channels (VR_EARLY64=0 for A/B): ring position handed back before the global stores
     int epi_direct; // K3 (VR_EPI_DIRECT): each lane stores its own pixel's 32 channels with two 256-bit stores, no staging transpose
     int l2_hint; // K3 (VR_L2HINT): 1 = newest source plane and the output evict_last, older source planes evict_first;
-                 // 2 / 3 = the first one / two source planes (the dense block's x) evict_last, everything else streams
+                 // 2 / 3 = the first one / two source planes (the dense block's x) evict_last, everything else streams;
+                 // 4 / 5 / 6 = the first two / first three / all source planes keep a FRACTION l2_frac of their lines
+                 // (evict_last, chosen by address) and stream the rest, so that the kept part fits the L2
+    float l2_frac;
     long long* dbg_cycles;  // optional: [0,256) SM cycles per CTA; [256, 496) CTA 0's per-stage issuer timestamps
 };
 

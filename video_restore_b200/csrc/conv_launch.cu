@@ -332,6 +332,11 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
             return e ? std::atoi(e) : 0;
         }();
         a.l2_hint = env_hint;
+        static const float env_frac = []() {
+            const char* e = std::getenv("VR_L2FRAC");
+            return e ? static_cast<float>(std::atof(e)) : 0.5f;
+        }();
+        a.l2_frac = env_frac;
         static const int env_early = []() {
             const char* e = std::getenv("VR_EARLY64");
             return e ? std::atoi(e) : 1;

@@ -331,6 +331,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// evict_last for `frac` of the lines (the hardware picks them by address, in sixteenths), evict_first for the rest: a tensor
+// larger than what the L2 can keep is then partly resident instead of thrashing as a whole
+__device__ __forceinline__ uint64_t l2_policy_keep_fraction(float frac) {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(frac));
+    return p;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -354,6 +361,11 @@ __device__ __forceinline__ void stg128_hint(void* gptr, const uint4& v, uint64_t
 __device__ __forceinline__ void stg256(void* gptr, const uint4& lo, const uint4& hi) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
                  "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg256_hint(void* gptr, const uint4& lo, const uint4& hi, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(gptr), "r"(lo.x), "r"(lo.y),
+                 "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void ldg256(const void* gptr, uint4& lo, uint4& hi) {
