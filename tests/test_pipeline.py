@@ -1,0 +1,315 @@
+"""Multi-GPU in-process pipeline (video_restore_b200/pipeline.py): chunk plan, ordered reassembly with bounded memory,
+boundary-frame hand-over. CPU tests drive the real scheduler with a stub restorer whose temporal stage is the oracle's;
+the GPU test runs two real restorers (two host threads) and compares with one restorer walking the clip in order."""
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from oracle import filters as OF
+from video_restore_b200.pipeline import (ArraySource, ListSink, NullSink, OrderedReassembler, SyntheticSource,
+                                         plan_chunks, run_pipeline)
+from video_restore_b200.restorer import FrameOpts
+
+
+class StubRestorer:
+    """x2 nearest 'upscale' + a per-frame tweak; temporal stage = oracle temporal_blend on the un-blended results."""
+    scale = 2
+    instances = []
+
+    def __init__(self, gpu_id, delay=0.0):
+        self.gpu_id, self.delay = gpu_id, delay
+        self.prev = None
+        self.closed = False
+        self.frames_done = 0
+        StubRestorer.instances.append(self)
+
+    def _up(self, f):
+        u = np.repeat(np.repeat(f, 2, axis=0), 2, axis=1).astype(np.int32)
+        return np.clip(u + (u[::-1] % 7) - 3, 0, 255).astype(np.uint8)
+
+    def temporal_reset(self):
+        self.prev = None
+
+    def temporal_get_prev(self, sH, sW):
+        assert self.prev is not None and self.prev.shape[:2] == (sH, sW)
+        return self.prev.copy()
+
+    def process_stream(self, frames, opts):
+        for f in frames:
+            if self.delay:
+                time.sleep(self.delay)
+            u = self._up(f)
+            out = u
+            if opts.temporal:
+                if self.prev is not None:
+                    out = OF.temporal_blend(u, self.prev, opts.temporal_alpha, opts.temporal_tau)
+                self.prev = u
+            self.frames_done += 1
+            yield out
+
+    def close(self):
+        self.closed = True
+
+
+def stub_blend(gpu_id):
+    return lambda cur, prev, alpha, tau: OF.temporal_blend(cur, prev, alpha, tau)
+
+
+def clip(n, h=12, w=16, seed=3):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    # slow drift + occasional jumps so that the temporal gate both fires and does not
+    return [np.clip(base.astype(np.int32) + (i % 5) * 2 + (40 if i % 7 == 0 else 0), 0, 255).astype(np.uint8) for i in range(n)]
+
+
+def sequential(frames, opts):
+    r = StubRestorer(-1)
+    return list(r.process_stream(iter(frames), opts))
+
+
+def test_plan_chunks_contiguous_and_chunked():
+    assert plan_chunks(10, 3) == [(0, 4, 0), (4, 7, 1), (7, 10, 2)]
+    assert plan_chunks(2, 4) == [(0, 1, 0), (1, 2, 1)]            # more GPUs than frames: empty ranges dropped
+    assert plan_chunks(10, 2, 4) == [(0, 4, 0), (4, 8, 1), (8, 10, 0)]
+    assert plan_chunks(0, 2, 4) == []
+    for total, g, c in [(37, 3, 5), (64, 8, 8), (5, 2, 1)]:
+        p = plan_chunks(total, g, c)
+        assert p[0][0] == 0 and p[-1][1] == total and all(a[1] == b[0] for a, b in zip(p, p[1:]))
+        assert all(w == i % g for i, (_, _, w) in enumerate(p))
+    with pytest.raises(ValueError):
+        plan_chunks(10, 0)
+    with pytest.raises(ValueError):
+        plan_chunks(10, 2, 0)
+
+
+@pytest.mark.parametrize("n,gpus,chunk", [(23, [0, 1], 4), (23, [0, 1, 2], None), (9, [0, 1, 2, 3], 1), (16, [0], 5),
+                                          (7, [0, 1, 2, 3, 4, 5, 6, 7], 2), (1, [0, 1], 3)])
+def test_pipeline_matches_sequential_with_temporal(n, gpus, chunk):
+    frames = clip(n)
+    opts = FrameOpts(temporal=True)
+    want = sequential(frames, opts)
+    sink = ListSink()
+    StubRestorer.instances.clear()
+    warm = n % 2 == 0
+    st = run_pipeline(ArraySource(frames), sink, lambda g: StubRestorer(g, delay=0.001 * (g % 3)), gpus, opts, chunk=chunk,
+                      temporal_blend=stub_blend, warmup=warm)
+    assert sink.order == list(range(n))
+    assert len(sink.frames) == n and all(np.array_equal(a, b) for a, b in zip(sink.frames, want))
+    assert st.frames == n and st.boundary_frames == st.chunks - 1
+    # no redundant upscales: every frame went through exactly one restorer once (+ one warm-up frame per restorer)
+    assert sum(r.frames_done for r in StubRestorer.instances) == n + (len(gpus) if warm else 0)
+    assert all(r.closed for r in StubRestorer.instances)
+
+
+def test_pipeline_without_temporal_has_no_boundary_traffic():
+    frames = clip(13)
+    opts = FrameOpts()
+    sink = ListSink()
+    st = run_pipeline(ArraySource(frames), sink, lambda g: StubRestorer(g), [0, 1, 2], opts, chunk=2, temporal_blend=stub_blend)
+    assert st.boundary_frames == 0 and sink.order == list(range(13))
+    assert all(np.array_equal(a, b) for a, b in zip(sink.frames, sequential(frames, opts)))
+
+
+def test_reassembly_memory_is_bounded():
+    """A fast worker cannot run more than `capacity` frames ahead of the writer."""
+    n, G, C = 40, 2, 4
+    frames = clip(n, 6, 8)
+
+    class SlowSink(ListSink):
+        def write(self, index, frame):
+            time.sleep(0.002)
+            super().write(index, frame)
+
+    sink = SlowSink()
+    st = run_pipeline(ArraySource(frames), sink, lambda g: StubRestorer(g), list(range(G)), FrameOpts(temporal=True), chunk=C,
+                      temporal_blend=stub_blend)
+    assert sink.order == list(range(n))
+    assert st.max_held <= G * C + G
+    with pytest.raises(ValueError):
+        run_pipeline(ArraySource(frames), ListSink(), lambda g: StubRestorer(g), [0, 1], FrameOpts(temporal=True), chunk=4,
+                     capacity=7, temporal_blend=stub_blend)
+    # without deferred head frames any ring size works: a tiny ring only serialises the workers
+    sink2 = ListSink()
+    st2 = run_pipeline(ArraySource(frames), sink2, lambda g: StubRestorer(g), [0, 1], FrameOpts(), chunk=4, capacity=2)
+    assert sink2.order == list(range(n)) and st2.max_held <= 2
+
+
+def test_reassembler_blocks_and_orders():
+    sink = ListSink()
+    ra = OrderedReassembler(sink, total=6, capacity=2)
+    f = np.zeros((2, 2, 3), np.uint8)
+    blocked = threading.Event()
+
+    def late():
+        ra.put(3, f + 3)      # 3 >= 0 + 2: must block until frames 0 and 1 are written
+        blocked.set()
+
+    t = threading.Thread(target=late)
+    t.start()
+    time.sleep(0.05)
+    assert not blocked.is_set()
+    ra.put(1, f + 1)
+    ra.put(0, f)
+    ra.put(2, f + 2)
+    t.join(2)
+    assert blocked.is_set()
+    ra.put(4, f + 4)
+    ra.put(5, f + 5)
+    ra.finish()
+    assert sink.order == [0, 1, 2, 3, 4, 5] and [int(a[0, 0, 0]) for a in sink.frames] == [0, 1, 2, 3, 4, 5]
+
+
+def test_worker_error_propagates_and_does_not_hang():
+    class Boom(StubRestorer):
+        def process_stream(self, frames, opts):
+            for i, f in enumerate(frames):
+                if self.gpu_id == 1 and i == 1:
+                    raise RuntimeError("boom")
+                yield self._up(f)
+
+    with pytest.raises(RuntimeError):
+        run_pipeline(ArraySource(clip(20)), NullSink(), lambda g: Boom(g), [0, 1], FrameOpts(temporal=True), chunk=3,
+                     temporal_blend=stub_blend)
+
+
+def test_synthetic_source_is_random_access():
+    src = SyntheticSource(8, 12, 5, seed=2)
+    a = list(src.reader().read_range(0, 5))
+    b = list(src.reader().read_range(3, 5))
+    assert len(src) == 5 and np.array_equal(a[3], b[0]) and np.array_equal(a[4], b[1])
+
+
+@pytest.mark.gpu
+def test_two_restorers_match_one_gpu():
+    from video_restore_b200.restorer import FrameRestorer
+    from video_restore_b200.synth import random_state_dict, synth_frame
+
+    name = "RealESRGAN_x4_v3"
+    sd = random_state_dict(name, seed=0)
+    frames = [synth_frame(40, 56, seed=9, index=i) for i in range(11)]
+    opts = FrameOpts(denoise=True, sharpen=0.3, clahe=True, temporal=True)
+    one = FrameRestorer(name, sd, tile=64, tile_pad=10, gpu_id=0)
+    one.temporal_reset()
+    want = [one.process_frame(f, opts) for f in frames]
+    one.close()
+    for gpus, chunk in (([0, 0], 3), ([0, 0, 0], None)):
+        sink = ListSink()
+        st = run_pipeline(ArraySource(frames), sink, lambda g: FrameRestorer(name, sd, tile=64, tile_pad=10, gpu_id=g), gpus,
+                          opts, chunk=chunk)
+        assert sink.order == list(range(len(frames)))
+        assert all(np.array_equal(a, b) for a, b in zip(sink.frames, want)), (gpus, chunk)
+        assert st.boundary_frames == st.chunks - 1
+
+
+def _write_clip(path, n, h=48, w=64):
+    import cv2
+
+    wr = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (w, h))
+    assert wr.isOpened()
+    for i in range(n):
+        wr.write(np.full((h, w, 3), 20 + 25 * i, np.uint8))
+    wr.release()
+
+
+def test_video_file_source_and_sink_roundtrip(tmp_path):
+    """cv2 decode -> chunked workers (each with its own VideoCapture, seeking to its chunk) -> ordered cv2 encode."""
+    import cv2
+
+    from video_restore_b200.pipeline import VideoFileSink, VideoFileSource
+
+    src_path, dst_path = tmp_path / "in.mp4", tmp_path / "out.mp4"
+    _write_clip(src_path, 9)
+    src = VideoFileSource(str(src_path))
+    assert len(src) == 9 and (src.height, src.width) == (48, 64) and abs(src.fps - 24.0) < 1e-3
+    st = run_pipeline(src, VideoFileSink(str(dst_path), src.fps), lambda g: StubRestorer(g), [0, 1, 2], FrameOpts(), chunk=2,
+                      temporal_blend=stub_blend)
+    assert st.frames == 9
+    cap = cv2.VideoCapture(str(dst_path))
+    means = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        assert f.shape == (96, 128, 3)
+        means.append(float(f.mean()))
+    assert len(means) == 9
+    assert all(b > a for a, b in zip(means, means[1:])), "frames must come out in source order"
+    with pytest.raises(OSError):
+        VideoFileSource(str(tmp_path / "missing.mp4"))
+
+
+@pytest.mark.gpu
+def test_cli_video_file_two_workers(tmp_path, capsys):
+    import cv2
+
+    from video_restore_b200.cli import main
+
+    src_path, dst_path = tmp_path / "in.mp4", tmp_path / "out.mp4"
+    _write_clip(src_path, 7)
+    assert main([str(src_path), str(dst_path), "--model", "RealESRGAN_x4_v3", "--quality", "fast", "--enhanced",
+                 "--gpus", "0", "0"]) == 0
+    assert "processed 7 frames" in capsys.readouterr().out
+    cap = cv2.VideoCapture(str(dst_path))
+    n = 0
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        assert f.shape == (192, 256, 3)
+        n += 1
+    assert n == 7
+    # directory mode
+    out_dir = tmp_path / "outs"
+    assert main([str(tmp_path), str(out_dir), "--model", "RealESRGAN_x4_v3", "--quality", "fast", "--batch", "--gpus", "0"]) == 0
+    assert (out_dir / "in_upscaled.mp4").exists()
+
+
+class StubZeroCopy(StubRestorer):
+    """Same arithmetic, but renders into the pipeline's buffer pool like FrameRestorer.process_stream(out_pool=...)."""
+    zero_copy_stream = True
+    allocs = 0
+
+    @staticmethod
+    def alloc_host(shape):
+        StubZeroCopy.allocs += 1
+        return np.empty(shape, np.uint8)
+
+    def temporal_get_prev(self, sH, sW, out=None):
+        if out is None:
+            return super().temporal_get_prev(sH, sW)
+        np.copyto(out, self.prev)
+        return out
+
+    def process_stream(self, frames, opts, out_pool=None):
+        for out in super().process_stream(frames, opts):
+            if out_pool is None:
+                yield out
+            else:
+                dst = out_pool.get(out.shape)
+                np.copyto(dst, out)
+                yield dst
+
+
+@pytest.mark.parametrize("gpus,chunk,temporal", [([0, 1], 4, True), ([0, 1, 2], 3, False), ([0], None, True)])
+def test_zero_copy_pool_matches_and_is_bounded(gpus, chunk, temporal):
+    n = 41
+    frames = clip(n, 6, 8)
+    opts = FrameOpts(temporal=temporal)
+    want = sequential(frames, opts)
+
+    class SlowSink(ListSink):
+        def write(self, index, frame):
+            time.sleep(0.001)
+            super().write(index, frame)
+
+    sink = SlowSink()
+    StubZeroCopy.allocs = 0
+    st = run_pipeline(ArraySource(frames), sink, lambda g: StubZeroCopy(g), gpus, opts, chunk=chunk, temporal_blend=stub_blend)
+    assert sink.order == list(range(n))
+    assert all(np.array_equal(a, b) for a, b in zip(sink.frames, want))
+    G = len(gpus)
+    C = chunk or n
+    cap = (G * C + G) if (temporal and G > 1) else max(min(G * C, 64), 4)
+    assert StubZeroCopy.allocs <= cap + 5 * G, "host frame memory must stay within the pool"

@@ -1,8 +1,10 @@
 """Command-line surface of the reference's video_upscaler.py (argparse at video_upscaler.py:649-682, presets at
 :687-701, config at :704-718), driving the B200 hot path. Only the flag surface and the per-frame stage are
 reproduced: the reference's ffmpeg decode/encode pipes, progress bar and audio mux (video_upscaler.py:143-281,
-:507-627) are out of scope. For convenience a minimal OpenCV VideoCapture/VideoWriter loop
-is provided when cv2 is importable, plus `--synthetic N` to run N generated frames without any video I/O.
+:507-627) are out of scope. Video I/O is OpenCV VideoCapture / VideoWriter, frames flow through
+the in-process multi-GPU pipeline of pipeline.py (one thread + restorer per `--gpus` id, contiguous frame chunks,
+ordered bounded reassembly: N2), `--batch` walks a directory (N4), `--synthetic N` runs N generated 720p frames
+without any video I/O.
 
 Flags added on top of the reference's parser are the README-only ones the north star names:
   --model RealESRGAN_x2plus (README.md:158), --denoise S, --sharpen A (README.md:140-141),
@@ -127,47 +129,62 @@ def make_restorer(cfg: OptimizedConfig, gpu_id: int, state_dict=None):
                          blend="gaussian" if cfg.seamless else "crop", gpu_id=gpu_id)
 
 
+VIDEO_EXTS = (".mp4", ".mkv", ".avi", ".mov", ".webm", ".m4v")  # the reference's batch filter, video_upscaler.py:727-731
+
+
+def _run_one(cfg: OptimizedConfig, opts, source, sink, chunk: int):
+    """One clip through the multi-GPU pipeline (pipeline.py): one host thread + restorer per GPU in cfg.gpu_ids,
+    contiguous frame chunks, one boundary frame per chunk for the temporal stage, ordered bounded reassembly."""
+    from .pipeline import run_pipeline
+
+    return run_pipeline(source, sink, lambda gpu_id: make_restorer(cfg, gpu_id), cfg.gpu_ids, opts, chunk=chunk)
+
+
 def main(argv=None) -> int:
     args = build_parser().parse_args(argv)
     cfg = config_from_args(args)
     opts = frame_opts_from_config(cfg)
     import torch
 
+    from .pipeline import NullSink, SyntheticSource, VideoFileSink, VideoFileSource
+
     if not cfg.gpu_ids:
         cfg.gpu_ids = list(range(torch.cuda.device_count()))
     if not cfg.gpu_ids:
         print("Error: No CUDA GPUs available")  # same failure as video_upscaler.py:140-141
         return 1
-    restorer = make_restorer(cfg, cfg.gpu_ids[0])
-    t0 = time.time()
-    n = 0
+    # frames per contiguous range: bounds the reorder ring in front of the sequential encoder (G * 16 frames); one GPU
+    # walks the clip as a single range
+    chunk = 16 if len(cfg.gpu_ids) > 1 else None
     if args.synthetic > 0:
-        from .synth import synth_frame
-        for i in range(args.synthetic):
-            restorer.process_frame(synth_frame(720, 1280, seed=1, index=i), opts)
-            n += 1
-    else:
-        import cv2
-        cap = cv2.VideoCapture(args.input)
-        if not cap.isOpened():
-            print(f"Error: cannot open {args.input}")
+        st = _run_one(cfg, opts, SyntheticSource(720, 1280, args.synthetic, seed=1, distinct=8), NullSink(), chunk)
+        print(f"processed {st.frames} frames in {st.seconds:.2f} s ({st.fps:.2f} fps) on {len(cfg.gpu_ids)} GPU(s); "
+              f"{st.boundary_frames} boundary frames exchanged; model set-up {st.setup_seconds:.1f} s")
+        return 0
+    jobs = []
+    if args.batch:  # directory mode, video_upscaler.py:723-746
+        in_dir, out_dir = Path(args.input), Path(args.output)
+        if not in_dir.is_dir():
+            print(f"Error: {in_dir} is not a directory")
             return 1
-        fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
-        writer = None
-        while True:
-            ok, frame = cap.read()
-            if not ok:
-                break
-            out = restorer.process_frame(frame, opts)
-            if writer is None:
-                writer = cv2.VideoWriter(args.output, cv2.VideoWriter_fourcc(*"mp4v"), fps, (out.shape[1], out.shape[0]))
-            writer.write(out)
-            n += 1
-        if writer is not None:
-            writer.release()
-    dt = time.time() - t0
-    print(f"processed {n} frames in {dt:.2f} s ({n / max(dt, 1e-9):.2f} fps)")
-    return 0
+        out_dir.mkdir(parents=True, exist_ok=True)
+        for f in sorted(in_dir.iterdir()):
+            if f.suffix.lower() in VIDEO_EXTS:
+                jobs.append((f, out_dir / f"{f.stem}_upscaled.mp4"))
+    else:
+        jobs.append((Path(args.input), Path(args.output)))
+    rc = 0
+    for src_path, dst_path in jobs:
+        try:
+            source = VideoFileSource(str(src_path))
+        except OSError as e:
+            print(f"Error: {e}")
+            rc = 1
+            continue
+        st = _run_one(cfg, opts, source, VideoFileSink(str(dst_path), source.fps), chunk)
+        print(f"{src_path.name}: processed {st.frames} frames in {st.seconds:.2f} s ({st.fps:.2f} fps) on "
+              f"{len(cfg.gpu_ids)} GPU(s)")
+    return rc
 
 
 if __name__ == "__main__":

@@ -23,7 +23,7 @@
 
 namespace vr {
 
-constexpr int kPairMaxSlots = 8;
+constexpr int kPairMaxSlots = 12;
 
 template <int N>
 struct PairTraits {

@@ -1,0 +1,496 @@
+"""In-process multi-GPU video pipeline: frame source -> per-GPU restorers -> ordered reassembly -> sink.
+
+Replaces, for the restoration stage only, the reference's reader thread / per-GPU worker threads / writer thread
+(video_upscaler.py:369-404 start-up, :406-451 reader, :453-488 workers, :507-567 writer) -- SURVEY.md 8(f) N1, N2:
+
+* threading model as the reference: ONE host thread per GPU, each with its own restorer (`self.models[gpu_id]`, :340);
+  ctypes releases the GIL inside the C-ABI calls, so the GPUs run concurrently;
+* work split: CONTIGUOUS frame ranges ("chunks") instead of the reference's `frame_idx % n_gpus` tag on a shared queue
+  (:437, which drops frames dequeued by the wrong worker, :471-473). Chunk c = frames [c*C, (c+1)*C) goes to GPU c % G.
+  With C = ceil(F / G) this is exactly the one-range-per-GPU sharding of `sharder.py`; a sequential encoder needs the
+  frames in order, so for it C is small and the ranges interleave;
+* temporal consistency across a chunk boundary WITHOUT any redundant upscale: out_t = blend(u_t, u_{t-1}) depends on
+  the previous frame's UN-blended result only (non-recursive, oracle/filters.py::temporal_blend). A worker therefore
+  runs its chunk with a reset temporal state -- the head frame passes through as u_first -- publishes its last
+  un-blended frame u_last for the next chunk, and finishes its own head frame with one stand-alone temporal kernel
+  once the previous chunk's u_last has arrived. Exactly one boundary frame per chunk crosses GPUs; results are
+  bit-identical to a single-GPU run (tests/test_pipeline.py);
+* ordered reassembly with bounded memory (the reference's PriorityQueue + sentinel/timeout logic, :535-567): workers
+  `put(i, frame)` into a ring of `capacity` frames and block while `i >= next_to_write + capacity`; one writer thread
+  hands frames to the sink strictly in order. capacity >= G*C is required (a chunk's head frame is written last) and
+  enforced.
+
+No CPU fallback: restorers are `FrameRestorer` instances (CUDA only); tests drive the same scheduler with a stub.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from dataclasses import dataclass, replace
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sources and sinks
+# ---------------------------------------------------------------------------------------------------------------
+class SyntheticSource:
+    """`n` generated frames (synth.synth_frame); random access, thread-safe. `distinct` > 0 generates only that many
+    different frames and cycles through them (frame generation is ~50 ms of numpy per 720p frame, more than a B200
+    needs to restore one)."""
+
+    def __init__(self, height: int, width: int, n: int, seed: int = 1, distinct: int = 0):
+        self.height, self.width, self.n, self.seed, self.distinct = height, width, n, seed, distinct
+        self.fps = 30.0
+        self._cache: dict = {}
+        self._lock = threading.Lock()
+
+    def __len__(self) -> int:
+        return self.n
+
+    def reader(self) -> "SyntheticSource":
+        return self
+
+    def _frame(self, i: int) -> np.ndarray:
+        from .synth import synth_frame
+
+        if self.distinct <= 0:
+            return synth_frame(self.height, self.width, seed=self.seed, index=i)
+        k = i % self.distinct
+        with self._lock:
+            if k not in self._cache:
+                self._cache[k] = synth_frame(self.height, self.width, seed=self.seed, index=k)
+            return self._cache[k]
+
+    def read_range(self, start: int, end: int):
+        for i in range(start, end):
+            yield self._frame(i)
+
+
+class ArraySource:
+    """Frames held in memory (tests, small clips)."""
+
+    def __init__(self, frames: Sequence[np.ndarray], fps: float = 30.0):
+        self.frames, self.fps = list(frames), fps
+
+    def __len__(self) -> int:
+        return len(self.frames)
+
+    def reader(self) -> "ArraySource":
+        return self
+
+    def read_range(self, start: int, end: int):
+        return iter(self.frames[start:end])
+
+
+class VideoFileSource:
+    """OpenCV-decoded video file (stands in for the reference's ffmpeg rawvideo pipe, :220-249). Every worker thread
+    gets its own `cv2.VideoCapture` (`reader()`), seeks to its chunk and decodes sequentially from there."""
+
+    def __init__(self, path: str):
+        import cv2
+
+        self.path = str(path)
+        cap = cv2.VideoCapture(self.path)
+        if not cap.isOpened():
+            raise OSError(f"cannot open {self.path}")
+        self.n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        self.fps = float(cap.get(cv2.CAP_PROP_FPS) or 30.0)
+        self.width = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+        self.height = int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+        cap.release()
+
+    def __len__(self) -> int:
+        return self.n
+
+    def reader(self) -> "_VideoReader":
+        return _VideoReader(self.path)
+
+
+class _VideoReader:
+    def __init__(self, path: str):
+        import cv2
+
+        self._cv2 = cv2
+        self.cap = cv2.VideoCapture(path)
+        self.pos = 0
+
+    def read_range(self, start: int, end: int):
+        if self.pos != start:
+            self.cap.set(self._cv2.CAP_PROP_POS_FRAMES, start)
+            self.pos = start
+        for _ in range(start, end):
+            ok, frame = self.cap.read()
+            if not ok:
+                return
+            self.pos += 1
+            yield frame
+
+
+class NullSink:
+    """Counts frames and keeps an order-sensitive checksum (benchmarks, tests)."""
+
+    def __init__(self):
+        self.count = 0
+        self.checksum = 0
+        self.order: List[int] = []
+
+    def write(self, index: int, frame: np.ndarray) -> None:
+        self.count += 1
+        self.order.append(index)
+        self.checksum = (self.checksum * 1000003 + int(frame[::97, ::89].astype(np.uint32).sum()) + index) % (1 << 61)
+
+    def close(self) -> None:
+        pass
+
+
+class ListSink:
+    def __init__(self):
+        self.frames: List[np.ndarray] = []
+        self.order: List[int] = []
+
+    def write(self, index: int, frame: np.ndarray) -> None:
+        self.order.append(index)
+        self.frames.append(frame.copy())
+
+    def close(self) -> None:
+        pass
+
+
+class VideoFileSink:
+    """cv2.VideoWriter (stands in for the reference's libx264 encoder pipe, :514-532)."""
+
+    def __init__(self, path: str, fps: float, fourcc: str = "mp4v"):
+        self.path, self.fps, self.fourcc = str(path), fps, fourcc
+        self.writer = None
+
+    def write(self, index: int, frame: np.ndarray) -> None:
+        import cv2
+
+        if self.writer is None:
+            self.writer = cv2.VideoWriter(self.path, cv2.VideoWriter_fourcc(*self.fourcc), self.fps,
+                                          (frame.shape[1], frame.shape[0]))
+            if not self.writer.isOpened():
+                raise OSError(f"cannot open {self.path} for writing")
+        self.writer.write(frame)
+
+    def close(self) -> None:
+        if self.writer is not None:
+            self.writer.release()
+            self.writer = None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# chunk plan
+# ---------------------------------------------------------------------------------------------------------------
+def plan_chunks(total: int, n_workers: int, chunk: Optional[int] = None) -> List[tuple]:
+    """[(start, end, worker)] covering [0, total): chunk c -> worker c % n_workers. chunk=None: one contiguous range
+    per worker (sizes differ by at most one frame, like sharder.shard_range)."""
+    if total < 0 or n_workers <= 0:
+        raise ValueError("bad total / worker count")
+    if chunk is None:
+        from .sharder import shard_range
+
+        out = []
+        for w in range(n_workers):
+            s, e = shard_range(total, w, n_workers)
+            if e > s:
+                out.append((s, e, w))
+        return out
+    if chunk <= 0:
+        raise ValueError("chunk must be positive")
+    return [(s, min(s + chunk, total), c % n_workers) for c, s in enumerate(range(0, total, chunk))]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# frame buffers
+# ---------------------------------------------------------------------------------------------------------------
+class BufferPool:
+    """At most `count` page-locked output frames, allocated on first use. Restorers render straight into them
+    (FrameRestorer.process_stream(out_pool=...)), the reassembler hands them to the sink and gives them back: no
+    per-frame copy, and the host memory of the whole pipeline is bounded by count * frame bytes."""
+
+    def __init__(self, count: int, alloc: Callable):
+        self.count, self._alloc = count, alloc
+        self._cv = threading.Condition()
+        self._free: List[np.ndarray] = []
+        self.allocated = 0
+        self._abort = False
+
+    def get(self, shape) -> np.ndarray:
+        shape = tuple(shape)
+        with self._cv:
+            while True:
+                if self._abort:
+                    raise RuntimeError("pipeline aborted")
+                for i, b in enumerate(self._free):
+                    if b.shape == shape:
+                        return self._free.pop(i)
+                if self.allocated < self.count:
+                    self.allocated += 1
+                    break
+                if self._free:  # another frame size (a new clip): drop a stale buffer and allocate
+                    self._free.pop()
+                    break
+                self._cv.wait(0.5)
+        return self._alloc(shape)
+
+    def release(self, buf: np.ndarray) -> None:
+        with self._cv:
+            self._free.append(buf)
+            self._cv.notify()
+
+    def abort(self) -> None:
+        with self._cv:
+            self._abort = True
+            self._cv.notify_all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ordered reassembly
+# ---------------------------------------------------------------------------------------------------------------
+class OrderedReassembler:
+    """Bounded reorder ring in front of a sequential sink. `put` copies the frame (restorers hand out views of pinned
+    buffers that are reused) and blocks while the index is more than `capacity` frames ahead of the writer."""
+
+    def __init__(self, sink, total: int, capacity: int):
+        if capacity < 1:
+            raise ValueError("capacity must be >= 1")
+        self.sink, self.total, self.capacity = sink, total, capacity
+        self._cv = threading.Condition()
+        self._slots: dict = {}
+        self._free: List[np.ndarray] = []
+        self._next = 0
+        self._error: Optional[BaseException] = None
+        self.max_held = 0
+        self._thread = threading.Thread(target=self._writer, name="vr-writer", daemon=True)
+        self._thread.start()
+
+    def put(self, index: int, frame: np.ndarray, release: Optional[Callable] = None) -> None:
+        """Without `release` the frame is copied (it may be a view of a buffer the producer reuses); with it the
+        reassembler takes the buffer over and calls release(frame) once the sink has written it."""
+        with self._cv:
+            while index >= self._next + self.capacity and self._error is None:
+                self._cv.wait(0.5)
+            if self._error is not None:
+                raise RuntimeError("reassembly aborted") from self._error
+            buf = None
+            if release is None and self._free and self._free[-1].shape == frame.shape:
+                buf = self._free.pop()
+        if release is None:
+            if buf is None:
+                buf = np.empty_like(frame)
+            np.copyto(buf, frame)
+        else:
+            buf = frame
+        with self._cv:
+            self._slots[index] = (buf, release)
+            self.max_held = max(self.max_held, len(self._slots))
+            self._cv.notify_all()
+
+    def abort(self, exc: BaseException) -> None:
+        with self._cv:
+            if self._error is None:
+                self._error = exc
+            self._cv.notify_all()
+
+    def _writer(self) -> None:
+        try:
+            while True:
+                with self._cv:
+                    while self._next not in self._slots and self._next < self.total and self._error is None:
+                        self._cv.wait(0.5)
+                    if self._error is not None or self._next >= self.total:
+                        return
+                    buf, release = self._slots.pop(self._next)
+                    idx = self._next
+                self.sink.write(idx, buf)
+                if release is not None:
+                    release(buf)
+                with self._cv:
+                    self._next += 1
+                    if release is None and len(self._free) < 4:
+                        self._free.append(buf)
+                    self._cv.notify_all()
+        except BaseException as e:  # noqa: BLE001 - surfaced to the workers and to finish()
+            self.abort(e)
+
+    def finish(self) -> None:
+        self._thread.join()
+        if self._error is not None:
+            raise RuntimeError("pipeline failed") from self._error
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# boundary frames
+# ---------------------------------------------------------------------------------------------------------------
+class _Boundaries:
+    """u_last of chunk c, published by its worker for the worker of chunk c + 1 (one frame per chunk boundary)."""
+
+    def __init__(self):
+        self._cv = threading.Condition()
+        self._frames: dict = {}
+        self._error = False
+
+    def publish(self, chunk_index: int, frame: np.ndarray) -> None:
+        with self._cv:
+            self._frames[chunk_index] = frame
+            self._cv.notify_all()
+
+    def take(self, chunk_index: int) -> np.ndarray:
+        with self._cv:
+            while chunk_index not in self._frames and not self._error:
+                self._cv.wait(0.5)
+            if self._error:
+                raise RuntimeError("pipeline aborted while waiting for a boundary frame")
+            return self._frames.pop(chunk_index)
+
+    def abort(self) -> None:
+        with self._cv:
+            self._error = True
+            self._cv.notify_all()
+
+
+@dataclass
+class PipelineStats:
+    frames: int = 0
+    seconds: float = 0.0
+    boundary_frames: int = 0
+    chunks: int = 0
+    max_held: int = 0
+    setup_seconds: float = 0.0
+
+    @property
+    def fps(self) -> float:
+        return self.frames / self.seconds if self.seconds > 0 else 0.0
+
+
+def _default_temporal_blend(gpu_id: int):
+    from .restorer import temporal_blend
+
+    return lambda cur, prev, alpha, tau: temporal_blend(cur, prev, alpha, tau, device=gpu_id)
+
+
+def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: Sequence[int], opts,
+                 chunk: Optional[int] = None, capacity: Optional[int] = None,
+                 temporal_blend: Optional[Callable[[int], Callable]] = None, warmup: bool = True) -> PipelineStats:
+    """Restore every frame of `source` into `sink` (in order) on the GPUs `gpu_ids` (one thread + one restorer each;
+    an id may repeat to run two restorers on one GPU). `make_restorer(gpu_id)` builds a FrameRestorer-like object
+    (process_stream, temporal_reset, temporal_get_prev, scale, close); `opts` is a FrameOpts.
+
+    chunk: frames per contiguous range; None = ceil(F / G) (one range per GPU, `sharder.py`'s split), which needs a
+    reorder ring of the whole video -- a sequential sink wants a small chunk (the CLI uses 8).
+    capacity: reorder-ring frames; with the temporal stage and more than one chunk the minimum is G * C (default
+    G * C + G), otherwise any value >= 1 works (default min(G * C, 64)).
+    warmup: run one frame through every restorer before the clock starts (counted as set-up)."""
+    total = len(source)
+    gpu_ids = list(gpu_ids)
+    if not gpu_ids:
+        raise ValueError("no GPUs given")
+    G = len(gpu_ids)
+    plan = plan_chunks(total, G, chunk)
+    C_max = max((e - s for s, e, _ in plan), default=1)
+    use_temporal = bool(getattr(opts, "temporal", False))
+    # a deferred head frame is written after the rest of its chunk: the ring must then hold one chunk per GPU
+    need = G * C_max if (use_temporal and len(plan) > 1) else 1
+    if capacity is None:
+        capacity = need + G if need > 1 else max(min(G * C_max, 64), 4)
+    if capacity < need:
+        raise ValueError(f"capacity {capacity} < {need}: a chunk's head frame is written last, so the ring must hold "
+                         f"one chunk per GPU")
+    reasm = OrderedReassembler(sink, total, capacity)
+    bounds = _Boundaries()
+    make_blend = temporal_blend or _default_temporal_blend
+    stats = PipelineStats(chunks=len(plan))
+    errors: List[BaseException] = []
+    lock = threading.Lock()
+
+    def worker(slot: int) -> None:
+        gpu = gpu_ids[slot]
+        restorer = None
+        try:
+            restorer = make_restorer(gpu)
+            blend = make_blend(gpu)
+            reader = source.reader()
+            zero_copy = bool(getattr(restorer, "zero_copy_stream", False))
+            if zero_copy:
+                with lock:
+                    if pool[0] is None:
+                        # ring + per worker: two frames in flight, one being handed over, the deferred head, a boundary frame
+                        pool[0] = BufferPool(capacity + 5 * G, restorer.alloc_host)
+            kw = {"out_pool": pool[0]} if zero_copy else {}
+            give_back = pool[0].release if zero_copy else None
+            if warmup and total > 0:
+                # first-use costs (activation buffers, tensor maps, the pinned frame rings) belong to the set-up
+                for out in restorer.process_stream(reader.read_range(plan[0][0], plan[0][0] + 1), opts, **kw):
+                    if give_back:
+                        give_back(out)
+            ready.wait()  # the clock starts when every GPU has its weights (model set-up is not frame throughput)
+            if slot == 0:
+                t_start[0] = time.perf_counter()
+            for ci, (s, e, w) in enumerate(plan):
+                if w != slot:
+                    continue
+                defer_head = use_temporal and ci > 0
+                head = None
+                if use_temporal:
+                    restorer.temporal_reset()
+                out_shape = None
+                for k, out in enumerate(restorer.process_stream(reader.read_range(s, e), opts, **kw)):
+                    out_shape = out.shape
+                    if k == 0 and defer_head:
+                        # u_first: passed through by the reset temporal stage; kept until the boundary frame is here
+                        head = out if zero_copy else out.copy()
+                    else:
+                        reasm.put(s + k, out, give_back)
+                if use_temporal and ci + 1 < len(plan) and out_shape is not None:
+                    if zero_copy:
+                        b = pool[0].get(out_shape)
+                        restorer.temporal_get_prev(out_shape[0], out_shape[1], out=b)
+                    else:
+                        b = restorer.temporal_get_prev(out_shape[0], out_shape[1])
+                    bounds.publish(ci, b)
+                if defer_head and head is not None:
+                    prev = bounds.take(ci - 1)
+                    with lock:
+                        stats.boundary_frames += 1
+                    reasm.put(s, blend(head, prev, opts.temporal_alpha, opts.temporal_tau))
+                    if zero_copy:
+                        give_back(head)
+                        give_back(prev)
+        except BaseException as exc:  # noqa: BLE001 - propagate to every thread, re-raised by the caller
+            with lock:
+                errors.append(exc)
+            ready.abort()
+            bounds.abort()
+            if pool[0] is not None:
+                pool[0].abort()
+            reasm.abort(exc)
+        finally:
+            if restorer is not None and hasattr(restorer, "close"):
+                restorer.close()
+
+    t0 = time.perf_counter()
+    t_start = [t0]
+    pool: List[Optional[BufferPool]] = [None]
+    ready = threading.Barrier(G)
+    threads = [threading.Thread(target=worker, args=(i,), name=f"vr-gpu{gpu_ids[i]}", daemon=True) for i in range(G)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        reasm.abort(errors[0])
+    try:
+        reasm.finish()
+    finally:
+        sink.close()
+    if errors:
+        raise errors[0]
+    t_end = time.perf_counter()
+    stats.seconds = t_end - t_start[0]
+    stats.setup_seconds = t_start[0] - t0
+    stats.frames = total
+    stats.max_held = reasm.max_held
+    return stats

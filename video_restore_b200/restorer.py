@@ -100,10 +100,14 @@ class FrameRestorer:
         _lib.check(rc, self._h)
         return out
 
-    def process_stream(self, frames, opts: FrameOpts | None = None):
+    zero_copy_stream = True  # process_stream accepts out_pool (pipeline.py hands frames to the encoder without a copy)
+
+    def process_stream(self, frames, opts: FrameOpts | None = None, out_pool=None):
         """Generator over restored frames, in order, with H2D / compute / D2H of neighbouring frames overlapped
         (vr_submit / vr_wait, two frames in flight). `frames` is any iterable of uint8 HxWx3 BGR arrays. Each yielded
-        array is a view of a pinned buffer that is overwritten three frames later: copy it to keep it longer."""
+        array is a view of a pinned buffer that is overwritten three frames later: copy it to keep it longer -- or
+        pass `out_pool` (an object with get(shape) -> page-locked uint8 array, may block): every frame is then written
+        into a buffer of the caller's, who owns it from the moment it is yielded."""
         o = (opts or FrameOpts()).to_c()
         n_slots = 3
         ring_in, ring_out = getattr(self, "_rings", ([], []))  # pinned rings are kept across calls (slow to allocate)
@@ -114,13 +118,13 @@ class FrameRestorer:
                 raise ValueError("frame must be uint8 HxWx3 BGR")
             H, W, _ = frame.shape
             s = self.scale
-            if not ring_in or ring_in[0].shape != frame.shape:
+            if not ring_in or ring_in[0].shape != frame.shape or (out_pool is None and not ring_out):
                 while pending:
                     t, out = pending.pop(0)
                     _lib.check(self._lib.vr_wait(self._h, t), self._h)
                     yield out
                 ring_in = [_lib.pinned_array((H, W, 3)) for _ in range(n_slots)]
-                ring_out = [_lib.pinned_array((H * s, W * s, 3)) for _ in range(n_slots)]
+                ring_out = [] if out_pool is not None else [_lib.pinned_array((H * s, W * s, 3)) for _ in range(n_slots)]
                 self._rings = (ring_in, ring_out)
             slot = i % n_slots
             if len(pending) >= 2:  # keep two in flight: the slot about to be reused has been handed out already
@@ -128,11 +132,12 @@ class FrameRestorer:
                 _lib.check(self._lib.vr_wait(self._h, t), self._h)
                 yield out
             np.copyto(ring_in[slot], frame)
+            dst = out_pool.get((H * s, W * s, 3)) if out_pool is not None else ring_out[slot]
             ticket = C.c_int64(0)
             _lib.check(self._lib.vr_submit(self._h, ring_in[slot].ctypes.data_as(C.c_void_p), H, W,
-                                           ring_in[slot].strides[0], ring_out[slot].ctypes.data_as(C.c_void_p),
-                                           ring_out[slot].strides[0], C.byref(o), C.byref(ticket)), self._h)
-            pending.append((int(ticket.value), ring_out[slot]))
+                                           ring_in[slot].strides[0], dst.ctypes.data_as(C.c_void_p),
+                                           dst.strides[0], C.byref(o), C.byref(ticket)), self._h)
+            pending.append((int(ticket.value), dst))
             i += 1
         while pending:
             t, out = pending.pop(0)
@@ -149,6 +154,11 @@ class FrameRestorer:
 
     def sync(self) -> None:
         _lib.check(self._lib.vr_sync(self._h), self._h)
+
+    @staticmethod
+    def alloc_host(shape) -> np.ndarray:
+        """uint8 array over page-locked memory (fast H2D / D2H staging, e.g. boundary frames in pipeline.py)."""
+        return _lib.pinned_array(tuple(shape))
 
     @property
     def stream(self) -> int:
@@ -167,11 +177,11 @@ class FrameRestorer:
             _lib.check(self._lib.vr_temporal_set_prev(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1],
                                                       a.strides[0], 0), self._h)
 
-    def temporal_get_prev(self, sH: int, sW: int, device_ptr: int | None = None):
+    def temporal_get_prev(self, sH: int, sW: int, device_ptr: int | None = None, out: np.ndarray | None = None):
         if device_ptr is not None:
             _lib.check(self._lib.vr_temporal_get_prev(self._h, C.c_void_p(int(device_ptr)), sH, sW, sW * 3, 1), self._h)
             return None
-        a = np.empty((sH, sW, 3), np.uint8)
+        a = out if out is not None else np.empty((sH, sW, 3), np.uint8)
         _lib.check(self._lib.vr_temporal_get_prev(self._h, a.ctypes.data_as(C.c_void_p), sH, sW, a.strides[0], 0),
                    self._h)
         return a
