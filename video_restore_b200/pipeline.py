@@ -236,6 +236,18 @@ class BufferPool:
                 self._cv.wait(0.5)
         return self._alloc(shape)
 
+    def reserve(self, shape, n: int) -> None:
+        """Allocate up to `n` more buffers now: page-locked allocations synchronise the device(s), so a pool that grows
+        while frames are in flight stalls every GPU for ~10 ms per buffer."""
+        shape = tuple(shape)
+        for _ in range(n):
+            with self._cv:
+                if self.allocated >= self.count:
+                    return
+                self.allocated += 1
+            buf = self._alloc(shape)
+            self.release(buf)
+
     def release(self, buf: np.ndarray) -> None:
         with self._cv:
             self._free.append(buf)
@@ -426,6 +438,9 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
                 for out in restorer.process_stream(reader.read_range(plan[0][0], plan[0][0] + 1), opts, **kw):
                     if give_back:
                         give_back(out)
+                        # this worker's share of the pool, up front (with deferred head frames the ring does fill up)
+                        want = (capacity + G - 1) // G + 5 if need > 1 else 8
+                        pool[0].reserve(out.shape, want - 1)
             ready.wait()  # the clock starts when every GPU has its weights (model set-up is not frame throughput)
             if slot == 0:
                 t_start[0] = time.perf_counter()
