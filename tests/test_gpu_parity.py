@@ -463,3 +463,66 @@ def test_cli_synthetic_run(gpu_lib, capsys):
     assert main(["in.mp4", "out.mp4", "--model", "RealESRGAN_x4_v3", "--quality", "fast", "--enhanced",
                  "--synthetic", "2"]) == 0
     assert "processed 2 frames" in capsys.readouterr().out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE full sizes (the oracle is too slow there)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", [FORCE_TILE, FORCE_PAIR])
+@pytest.mark.parametrize("cin,cout", [(160, 32), (192, 64)])
+def test_conv_720p_scaling_by_powers_of_two_is_exact(gpu_lib, kernel, cin, cout):
+    """Linearity at the headline size (720 x 1280, the dense block's widest layers): multiplying the input by 2 and the
+    bias by 2 is exact in fp16 / fp32, so every output must double bit for bit -- whatever the summation order."""
+    from video_restore_b200 import _lib
+
+    rng = np.random.default_rng(21)
+    H, W = 720, 1280
+    x = (rng.standard_normal((H, W, cin)) * 0.25).astype(np.float16).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(9 * cin)).astype(np.float16).astype(np.float32)
+    b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    y1, _ = _lib.conv3x3(x, w, b, flags=kernel)
+    y2, _ = _lib.conv3x3(x * 2.0, w, b * 2.0, flags=kernel)
+    assert np.isfinite(y1).all() and y1.std() > 0.1
+    normal = np.abs(y1) >= 2.0 ** -13  # below that the fp16 result is subnormal: fixed spacing, doubling is not exact
+    assert normal.mean() > 0.999
+    assert np.array_equal(y2[normal], y1[normal] * 2.0)
+    assert np.abs(y2[~normal] - 2.0 * y1[~normal]).max(initial=0.0) <= 2.0 ** -23
+    # and a second run of the same launch is bit-identical (no race between the 140 CTAs / 70 clusters)
+    y1b, _ = _lib.conv3x3(x, w, b, flags=kernel)
+    assert np.array_equal(y1, y1b)
+
+
+def test_filters_2880p_properties(gpu_lib):
+    """Enhancement kernels on a 5120 x 2880 frame (configs[3] output size): identities and integer invariants."""
+    from video_restore_b200 import restorer as R
+
+    small = synth_frame(720, 1280, seed=31)
+    f = np.ascontiguousarray(np.repeat(np.repeat(small, 4, axis=0), 4, axis=1))
+    f[::7, ::5] = 255 - f[::7, ::5]  # break the 4 x 4 blocks
+    assert f.shape == (2880, 5120, 3)
+    # unsharp with amount 0 is the identity ((1 + 0) x - 0 blur, rounded)
+    assert np.array_equal(R.unsharp_mask(f, 0.0), f)
+    # a flat frame is a fixed point of the blur, hence of the unsharp mask, and of the bilateral filter
+    flat = np.full((2880, 5120, 3), 77, np.uint8)
+    assert np.array_equal(R.unsharp_mask(flat, 0.7), flat)
+    assert np.array_equal(R.bilateral_filter(flat[:720, :1280]), flat[:720, :1280])
+    # temporal: prev == cur passes through; a frame further than tau away everywhere is not blended
+    assert np.array_equal(R.temporal_blend(f, f), f)
+    far = (f.astype(np.int32) + 128) % 256
+    assert np.array_equal(R.temporal_blend(f, far.astype(np.uint8), 0.2, 12.0), f)
+    # CLAHE: every tile histogram sums to the tile area after clipping + redistribution; LUTs are monotone
+    out, hist, lut = R.clahe_bgr(f, 2.0, 8, return_tables=True)
+    assert hist.shape == (64, 256) and (hist.sum(axis=1) == (2880 // 8) * (5120 // 8)).all()
+    assert (np.diff(lut.astype(np.int32), axis=1) >= 0).all()
+    assert out.shape == f.shape and out.std() > 0
+
+
+def test_tile_grid_full_sizes(gpu_lib):
+    """Tile tables (integer, bit-exact) at every BASELINE frame size / preset, against the oracle's tile loop."""
+    from oracle.realesrganer import tile_grid as o_tile_grid
+    from video_restore_b200 import restorer as R
+
+    for H, W, tile, pad, s in [(720, 1280, 512, 64, 4), (720, 1280, 1536, 10, 4), (1080, 1920, 512, 32, 2),
+                               (1080, 1920, 1024, 10, 4), (1080, 1920, 512, 32, 4), (480, 854, 1024, 16, 4),
+                               (256, 256, 128, 16, 4), (2160, 3840, 512, 32, 4)]:
+        assert np.array_equal(R.tile_grid(H, W, tile, pad, s), o_tile_grid(H, W, tile, pad, s)), (H, W, tile)
