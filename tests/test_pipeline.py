@@ -313,3 +313,19 @@ def test_zero_copy_pool_matches_and_is_bounded(gpus, chunk, temporal):
     C = chunk or n
     cap = (G * C + G) if (temporal and G > 1) else max(min(G * C, 64), 4)
     assert StubZeroCopy.allocs <= cap + 5 * G, "host frame memory must stay within the pool"
+
+
+def test_source_shorter_than_announced_does_not_hang():
+    """Container frame counts are estimates: a source that runs dry early truncates the output instead of stalling."""
+    class Liar(ArraySource):
+        def __len__(self):
+            return len(self.frames) + 5
+
+    frames = clip(14)
+    opts = FrameOpts(temporal=True)
+    want = sequential(frames, opts)
+    for gpus, chunk in (([0, 1], 4), ([0], None), ([0, 1, 2], 2)):
+        sink = ListSink()
+        st = run_pipeline(Liar(frames), sink, lambda g: StubZeroCopy(g), gpus, opts, chunk=chunk, temporal_blend=stub_blend)
+        assert st.frames == 14 and sink.order == list(range(14))
+        assert all(np.array_equal(a, b) for a, b in zip(sink.frames, want))

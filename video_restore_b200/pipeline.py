@@ -283,10 +283,14 @@ class OrderedReassembler:
         """Without `release` the frame is copied (it may be a view of a buffer the producer reuses); with it the
         reassembler takes the buffer over and calls release(frame) once the sink has written it."""
         with self._cv:
-            while index >= self._next + self.capacity and self._error is None:
+            while index >= self._next + self.capacity and index < self.total and self._error is None:
                 self._cv.wait(0.5)
             if self._error is not None:
                 raise RuntimeError("reassembly aborted") from self._error
+            if index >= self.total:  # the source ended early (truncate): frames past the end are dropped
+                if release is not None:
+                    release(frame)
+                return
             buf = None
             if release is None and self._free and self._free[-1].shape == frame.shape:
                 buf = self._free.pop()
@@ -305,6 +309,18 @@ class OrderedReassembler:
         with self._cv:
             if self._error is None:
                 self._error = exc
+            self._cv.notify_all()
+
+    def truncate(self, total: int) -> None:
+        """The source delivered fewer frames than it announced (container frame counts are estimates): stop after
+        frame total - 1 instead of waiting for frames that will never come."""
+        with self._cv:
+            if total < self.total:
+                self.total = total
+                for i in [k for k in self._slots if k >= total]:
+                    buf, release = self._slots.pop(i)
+                    if release is not None:
+                        release(buf)
             self._cv.notify_all()
 
     def _writer(self) -> None:
@@ -452,13 +468,19 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
                 if use_temporal:
                     restorer.temporal_reset()
                 out_shape = None
+                got = 0
                 for k, out in enumerate(restorer.process_stream(reader.read_range(s, e), opts, **kw)):
                     out_shape = out.shape
+                    got = k + 1
                     if k == 0 and defer_head:
                         # u_first: passed through by the reset temporal stage; kept until the boundary frame is here
                         head = out if zero_copy else out.copy()
                     else:
                         reasm.put(s + k, out, give_back)
+                if got < e - s:
+                    reasm.truncate(s + got)
+                if use_temporal and ci + 1 < len(plan) and out_shape is None:
+                    bounds.publish(ci, None)  # nothing decoded: the next chunk (past the end) must not wait
                 if use_temporal and ci + 1 < len(plan) and out_shape is not None:
                     if zero_copy:
                         b = pool[0].get(out_shape)
@@ -468,12 +490,15 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
                     bounds.publish(ci, b)
                 if defer_head and head is not None:
                     prev = bounds.take(ci - 1)
-                    with lock:
-                        stats.boundary_frames += 1
-                    reasm.put(s, blend(head, prev, opts.temporal_alpha, opts.temporal_tau))
-                    if zero_copy:
-                        give_back(head)
-                        give_back(prev)
+                    if prev is None:
+                        reasm.put(s, head, give_back)
+                    else:
+                        with lock:
+                            stats.boundary_frames += 1
+                        reasm.put(s, blend(head, prev, opts.temporal_alpha, opts.temporal_tau))
+                        if zero_copy:
+                            give_back(head)
+                            give_back(prev)
         except BaseException as exc:  # noqa: BLE001 - propagate to every thread, re-raised by the caller
             with lock:
                 errors.append(exc)
@@ -506,6 +531,6 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
     t_end = time.perf_counter()
     stats.seconds = t_end - t_start[0]
     stats.setup_seconds = t_start[0] - t0
-    stats.frames = total
+    stats.frames = reasm.total
     stats.max_held = reasm.max_held
     return stats
