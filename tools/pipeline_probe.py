@@ -32,7 +32,8 @@ class Timed(NullSink):
     def write(self, i, f):
         t = time.perf_counter(); super().write(i, f); self.t += time.perf_counter() - t
 
-for label, kw in (("pipeline zero-copy", {}), ("pipeline, no checksum sink", {"nosum": True})):
+for label, kw in (("pipeline zero-copy", {}), ("pipeline zero-copy again", {}), ("pipeline, no checksum sink", {"nosum": True}),
+                  ("pipeline zero-copy, third time", {})):
     sink = Timed()
     if kw.get("nosum"):
         sink.write = lambda i, f, s=sink: (s.order.append(i), setattr(s, "count", s.count + 1))

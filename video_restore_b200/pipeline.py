@@ -258,6 +258,15 @@ class BufferPool:
             self._abort = True
             self._cv.notify_all()
 
+    def close(self) -> None:
+        """Drop the buffers now. Page-locked memory is returned by a finalizer (cudaFreeHost synchronises the device):
+        left to the garbage collector it would fire in the middle of somebody's next run."""
+        import gc
+
+        with self._cv:
+            self._free.clear()
+        gc.collect()
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # ordered reassembly
@@ -533,4 +542,7 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
     stats.setup_seconds = t_start[0] - t0
     stats.frames = reasm.total
     stats.max_held = reasm.max_held
+    if pool[0] is not None:
+        reasm._free.clear()
+        pool[0].close()
     return stats

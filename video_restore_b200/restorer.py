@@ -200,6 +200,7 @@ class FrameRestorer:
         if getattr(self, "_h", None) and self._h.value:
             self._lib.vr_destroy(self._h)
             self._h = C.c_void_p()
+        self._rings = ([], [])  # the pinned frame rings go back now, not whenever the collector finds them
 
     def __del__(self):
         try:
