@@ -329,3 +329,13 @@ def test_source_shorter_than_announced_does_not_hang():
         st = run_pipeline(Liar(frames), sink, lambda g: StubZeroCopy(g), gpus, opts, chunk=chunk, temporal_blend=stub_blend)
         assert st.frames == 14 and sink.order == list(range(14))
         assert all(np.array_equal(a, b) for a, b in zip(sink.frames, want))
+
+
+def test_restorer_construction_failure_propagates():
+    def make(g):
+        if g == 1:
+            raise ValueError("no such device")
+        return StubRestorer(g)
+
+    with pytest.raises(ValueError, match="no such device"):
+        run_pipeline(ArraySource(clip(10)), NullSink(), make, [0, 1, 2], FrameOpts(temporal=True), chunk=2, temporal_blend=stub_blend)

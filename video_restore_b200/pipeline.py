@@ -529,14 +529,16 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
         t.start()
     for t in threads:
         t.join()
-    if errors:
+    if errors:  # the first failure wins; BrokenBarrierError / "aborted" from the other threads are its echoes
         reasm.abort(errors[0])
+        reasm._thread.join()
+        sink.close()
+        first = next((e for e in errors if not isinstance(e, threading.BrokenBarrierError)), errors[0])
+        raise first
     try:
         reasm.finish()
     finally:
         sink.close()
-    if errors:
-        raise errors[0]
     t_end = time.perf_counter()
     stats.seconds = t_end - t_start[0]
     stats.setup_seconds = t_start[0] - t0
