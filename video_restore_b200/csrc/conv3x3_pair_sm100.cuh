@@ -103,6 +103,24 @@ __device__ __forceinline__ void epi_stage32(const float* v, uint32_t stg_s, int 
     for (int u = 0; u < 4; ++u) ptx::sts128(stg_s + lane * (N * 2) + (((g * 4 + u) ^ swz_w) << 4), pack8(v + u * 8));
 }
 
+// pair_release with eight registers of bias in flight instead of 32 (for the path that holds a whole 64-column row)
+template <int N>
+__device__ __forceinline__ void pair_release_lean(uint32_t t_main, uint32_t t_mir, const float* s_bias, int lane, uint32_t release_addr) {
+#pragma unroll
+    for (int q = 0; q < N / 8; ++q) {
+        const float4 lo = *reinterpret_cast<const float4*>(s_bias + q * 8), hi = *reinterpret_cast<const float4*>(s_bias + q * 8 + 4);
+        ptx::tmem_st8(t_main + q * 8, lo, hi);
+    }
+    if (t_mir != 0xffffffffu) {
+#pragma unroll
+        for (int g = 0; g < N / 32; ++g) ptx::tmem_st32_zero(t_mir + g * 32);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive_cluster(release_addr);
+}
+
 // One output row x 32 pixels of this warp's lane quarter: accumulators (bias included; + mirror block when t_mir != ~0u) ->
 // activation -> residuals -> fp16 -> swizzled staging -> coalesced stores. Returns true when the ring position has already
 // been handed back (otherwise the caller does it).
@@ -220,14 +238,50 @@ __device__ __forceinline__ bool epi_row_pair(const ConvArgs& a, uint32_t t_main,
 // store fills whole 32-byte sectors, and the shared-memory traffic of the transpose (16 KB written + 16 KB read per row and
 // CTA at N = 64) is gone. That traffic matters: the MMAs alone read 5.5 KB (N = 32) / 7 KB (N = 64) of operands per 48 / 96
 // cycles from shared memory, 90 % / 57 % of its 128 B/cycle, and the TMA writes the activations on top.
-template <int N>
+template <int N, bool kNoRes>
 __device__ __forceinline__ bool epi_row_pair_direct(const ConvArgs& a, uint32_t t_main, uint32_t t_mir, int lane, int x_base, int y, bool gap,
                                                     const float* s_bias, const float* s_neg, int amode, uint32_t release_addr) {
     constexpr int kG = N / 32;
     const int x = x_base + lane;
     const bool inb = x < a.W;
     const size_t p = static_cast<size_t>(y) * a.W + x;
-    const bool has1 = a.res1 != nullptr, has2 = a.res2 != nullptr;
+    const bool has1 = !kNoRes && a.res1 != nullptr, has2 = !kNoRes && a.res2 != nullptr;
+    if constexpr (N == 64 && kNoRes) {
+        // Layers without residual operands (SRVGG body, conv_hr) have their own instantiation: without the residual registers
+        // the whole 64-column row fits, both TMEM loads are issued together and the ring position goes back right after
+        // them, before any arithmetic (a.early64 == 2).
+        if (a.early64 == 2) {
+            uint32_t acc[N];
+            ptx::tmem_ld32_issue(t_main, acc);
+            ptx::tmem_ld32_issue(t_main + 32, acc + 32);
+            ptx::tmem_ld32_wait(acc);
+            ptx::tmem_ld32_wait(acc + 32);
+            if (t_mir != 0xffffffffu) {
+#pragma unroll
+                for (int g = 0; g < kG; ++g) {
+                    float r1[32];
+                    ptx::tmem_ld32(t_mir + g * 32, r1);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[g * 32 + j] = __float_as_uint(__uint_as_float(acc[g * 32 + j]) + r1[j]);
+                }
+            }
+            pair_release_lean<N>(t_main, t_mir, s_bias, lane, release_addr);
+            const bool st = inb && !(a.flags & FLAG_SKIP_B);
+#pragma unroll
+            for (int g = 0; g < kG; ++g) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gap ? 0.f : __uint_as_float(acc[g * 32 + j]);
+                epi_act32(v, amode, a.slope, s_neg + g * 32);
+                if (st) {
+                    __half* o = a.out + chan_off(p, a.out_cstride, a.out_pstride, a.out_coff + g * 32);
+                    ptx::stg256(o, pack8(v), pack8(v + 8));
+                    ptx::stg256(o + 16, pack8(v + 16), pack8(v + 24));
+                }
+            }
+            return true;
+        }
+    }
     uint4 q1[kG * 4], q2[kG * 4];
     if (inb && has1) {
 #pragma unroll
@@ -346,7 +400,7 @@ __device__ __forceinline__ int pair_rows(const ConvArgs& a, int item) {  // rows
     return n0 > n1 ? n0 : n1;
 }
 
-template <int N, bool kDirect>
+template <int N, bool kDirect, bool kNoRes = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairTraits<N>::kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     using T = PairTraits<N>;
@@ -569,7 +623,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) 
                     const int y = y0 + l - 2;
                     bool gap = xgap;
                     for (int j = 0; j < a.ngy; ++j) gap |= ((y >> a.gshift) == a.gy[j]);
-                    if constexpr (kDirect) released = epi_row_pair_direct<N>(a, t_main, t_mir, lane, x_base, y, gap, s_bias, s_neg, amode, lead_tempty + m * 8);
+                    if constexpr (kDirect) released = epi_row_pair_direct<N, kNoRes>(a, t_main, t_mir, lane, x_base, y, gap, s_bias, s_neg, amode, lead_tempty + m * 8);
                     else released = epi_row_pair<N>(a, t_main, t_mir, stg_s, lane, x_base, y, gap, s_bias, s_neg, amode, lead_tempty + m * 8);
                 }
                 if (!released) pair_release<N>(t_main, t_mir, s_bias, lane, lead_tempty + m * 8);

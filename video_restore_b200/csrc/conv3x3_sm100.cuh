@@ -95,7 +95,8 @@ struct ConvArgs {
     int band, nbands;
     int nsplit;  // 1, or 2: the layer's 2N output channels are computed as two independent N-channel halves
     int unit;    // K3: boxes per issuer hand-over
-    int early64; // K3, 64 output channels (VR_EARLY64=0 for A/B): ring position handed back before the global stores
+    int early64; // K3, 64 output channels (VR_EARLY64): ring position handed back 0 = after the stores, 1 = before them,
+                 // 2 (default) = additionally right after the TMEM loads in the instantiation for layers without residuals
     int epi_direct; // K3 (VR_EPI_DIRECT): each lane stores its own pixel's 32 channels with two 256-bit stores, no staging transpose
     int l2_hint; // K3 (VR_L2HINT): 1 = newest source plane and the output evict_last, older source planes evict_first;
                  // 2 / 3 = the first one / two source planes (the dense block's x) evict_last, everything else streams;

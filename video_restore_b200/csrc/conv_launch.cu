@@ -316,12 +316,16 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     int nslots = (T::kBudget + T::kStgBytes - stg_bytes - w_bytes) / T::kASlot;
     if (nslots < T::kMinSlots) return 1;
     if (nslots > kPairMaxSlots) nslots = kPairMaxSlots;
-    auto kern = a.epi_direct ? conv3x3_pair_kernel<N, true> : conv3x3_pair_kernel<N, false>;
-    static bool attr_done[2][64] = {};
-    if (!attr_done[a.epi_direct][dev.ordinal & 63]) {
+    // layers without residual operands get the instantiation that has no residual registers (N = 64: early ring release)
+    const bool nores = a.epi_direct && !a.res1 && !a.res2;
+    auto kern = nores ? conv3x3_pair_kernel<N, true, true>
+                      : (a.epi_direct ? conv3x3_pair_kernel<N, true, false> : conv3x3_pair_kernel<N, false, false>);
+    const int variant = nores ? 2 : a.epi_direct;
+    static bool attr_done[3][64] = {};
+    if (!attr_done[variant][dev.ordinal & 63]) {
         VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kBudget + T::kStgBytes + 1024),
                       dev.err);
-        attr_done[a.epi_direct][dev.ordinal & 63] = true;
+        attr_done[variant][dev.ordinal & 63] = true;
     }
     a.nsplit = 1;
     a.wpack = w.wpair;
@@ -339,7 +343,7 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
         a.l2_frac = env_frac;
         static const int env_early = []() {
             const char* e = std::getenv("VR_EARLY64");
-            return e ? std::atoi(e) : 1;
+            return e ? std::atoi(e) : 2;
         }();
         a.early64 = env_early;
     }

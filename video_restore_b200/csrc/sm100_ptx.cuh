@@ -251,6 +251,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
           "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
         : "memory");
 }
+// 32 lanes x 8 consecutive columns <- lo, hi (a quarter of tmem_st32: a quarter of the register pressure)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& lo, const float4& hi) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(lo.x), "f"(lo.y),
+                 "f"(lo.z), "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
+                 : "memory");
+}
 // 32 lanes x 32 consecutive columns <- 0 (the issuing warp's lane quarter); tmem_st_wait() before signalling other threads
 __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
     const uint32_t z = 0u;
