@@ -18,6 +18,9 @@
 // Synchronisation: each CTA's producer loads its own strip; both count their bytes on the LEADER's full barrier. The
 // leader's commits are multicast (slot release and accumulator-ready barriers exist in both CTAs); both CTAs' epilogue
 // warps arrive on the leader's accumulator-free barriers (remote mbarrier arrive). Warp roles as in K1 / K2.
+// Instantiations: kDirect = epilogue with direct 256-bit stores (default; false = staged through shared memory, for
+// outputs that are not 32-channel groups and for A/B runs); kNoRes = layer without residual operands (no residual
+// registers: 112 / 156 instead of 156 / 168, which is what lets N = 64 release its ring position before the arithmetic).
 #pragma once
 #include "conv3x3_roll_sm100.cuh"
 

@@ -1,5 +1,6 @@
-// Host side of K1 / K2: weight repacking into the swizzled shared-memory image, TMA tensor-map construction,
-// kernel selection and launch. See conv3x3_sm100.cuh for the kernel.
+// Host side of the convolution kernels K1 / K2 / K3: weight repacking into the swizzled shared-memory images, TMA
+// tensor-map construction, kernel selection and launch. Kernels: conv3x3_sm100.cuh (K1), conv3x3_roll_sm100.cuh (K2),
+// conv3x3_pair_sm100.cuh (K3, the default for 32 / 64 output channels).
 #include "conv3x3_pair_sm100.cuh"
 #include "vr_common.h"
 
