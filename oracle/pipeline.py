@@ -59,6 +59,9 @@ class OracleRestorer:
     def temporal_set_prev(self, up_prev):
         self.prev_up = np.ascontiguousarray(up_prev, dtype=np.uint8).copy()
 
+    def temporal_get_prev(self, sH=None, sW=None):
+        return self.prev_up.copy()
+
     def upscale_only(self, frame: np.ndarray, opts: FrameOpts) -> np.ndarray:
         """Everything except the temporal blend: returns up_t."""
         f = frame

@@ -54,7 +54,7 @@ def _opts():
     return FrameOpts(denoise=True, sharpen=0.3, clahe=True, temporal=True, temporal_tau=40.0)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, defer_head=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(1)
@@ -62,14 +62,23 @@ def _worker(rank, world, port, out_dir):
     frames = _frames()
     results = {}
     sh = FrameRangeSharder(rank, world, N_FRAMES)
-    n = sh.run(_make_oracle(), lambda i: frames[i], lambda i, o: results.__setitem__(i, o), _opts())
+    orc = _make_oracle()
+    calls = [0]
+    inner = orc.upscale_only
+    orc.upscale_only = lambda f, o: (calls.__setitem__(0, calls[0] + 1), inner(f, o))[1]
+    from oracle import filters as OF
+    n = sh.run(orc, lambda i: frames[i], lambda i, o: results.__setitem__(i, o), _opts(), defer_head=defer_head,
+               temporal_blend=OF.temporal_blend)
     assert n == len(results)
+    # the boundary protocol of step 1 costs one extra upscale per sending rank; the deferred head costs none
+    assert calls[0] == n + (0 if defer_head or rank == world - 1 else 1)
     np.savez(Path(out_dir) / f"rank{rank}.npz", **{str(k): v for k, v in results.items()})
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_shards_equal_one_shard(tmp_path):
+@pytest.mark.parametrize("world,defer_head", [(2, False), (2, True), (3, True)])
+def test_two_shards_equal_one_shard(tmp_path, world, defer_head):
     torch.set_num_threads(2)
     frames = _frames()
     single = {}
@@ -86,9 +95,9 @@ def test_two_shards_equal_one_shard(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), defer_head), nprocs=world, join=True)
     merged = {}
-    for r in range(2):
+    for r in range(world):
         z = np.load(tmp_path / f"rank{r}.npz")
         merged.update({int(k): z[k] for k in z.files})
     assert sorted(merged) == list(range(N_FRAMES))

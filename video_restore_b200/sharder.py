@@ -12,6 +12,12 @@ temporal-consistency stage, which needs up_{t-1} -- the previous frame's UN-blen
 
 Because the temporal stage is non-recursive, the sharded result is bit-identical to the single-GPU run.
 One process per GPU (torchrun); `torch.distributed` is plumbing only (send/recv of one frame per shard).
+
+`run(..., defer_head=True)` is the variant without the redundant upscale of step 1 (the one pipeline.py uses in-process):
+every rank walks its range with a RESET temporal state, so its head frame comes out un-blended (u_first) and is held back;
+at the end it sends its last un-blended frame (the restorer's temporal state) to rank g+1, receives rank g-1's, and finishes
+the head frame with one stand-alone temporal blend. Same single transfer per boundary, same bits, one frame less work per
+shard; the head frame of a shard is delivered last (put_frame is called out of order for it).
 """
 from __future__ import annotations
 
@@ -82,8 +88,28 @@ class FrameRangeSharder:
         else:
             restorer.temporal_reset()
 
-    def run(self, restorer, get_frame, put_frame, opts) -> int:
-        self.exchange_boundary(restorer, get_frame, opts)
-        for i in range(self.start, self.end):
+    def run(self, restorer, get_frame, put_frame, opts, defer_head: bool = False, temporal_blend: Callable | None = None) -> int:
+        """`temporal_blend(cur, prev, alpha, tau)` finishes a deferred head frame; default: the CUDA stand-alone kernel
+        (video_restore_b200.restorer.temporal_blend), tests pass the oracle's."""
+        if not (defer_head and opts.temporal and self.world > 1):
+            self.exchange_boundary(restorer, get_frame, opts)
+            for i in range(self.start, self.end):
+                put_frame(i, restorer.process_frame(get_frame(i), opts))
+            return self.end - self.start
+        n = self.end - self.start
+        if n == 0:
+            raise ValueError("empty shard: need total_frames >= world size when the temporal stage is on")
+        restorer.temporal_reset()
+        head = restorer.process_frame(get_frame(self.start), opts)  # reset state: passes through un-blended
+        for i in range(self.start + 1, self.end):
             put_frame(i, restorer.process_frame(get_frame(i), opts))
-        return self.end - self.start
+        if self.rank < self.world - 1:
+            self._send(restorer.temporal_get_prev(head.shape[0], head.shape[1]), self.rank + 1)
+        if self.rank > 0:
+            prev = self._recv(head.shape, self.rank - 1)
+            if temporal_blend is None:
+                from .restorer import temporal_blend as _tb
+                temporal_blend = _tb
+            head = temporal_blend(head, prev, opts.temporal_alpha, opts.temporal_tau)
+        put_frame(self.start, head)
+        return n
