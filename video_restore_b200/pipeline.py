@@ -417,7 +417,7 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
     (process_stream, temporal_reset, temporal_get_prev, scale, close); `opts` is a FrameOpts.
 
     chunk: frames per contiguous range; None = ceil(F / G) (one range per GPU, `sharder.py`'s split), which needs a
-    reorder ring of the whole video -- a sequential sink wants a small chunk (the CLI uses 8).
+    reorder ring of the whole video -- a sequential sink wants a small chunk (the CLI uses 16).
     capacity: reorder-ring frames; with the temporal stage and more than one chunk the minimum is G * C (default
     G * C + G), otherwise any value >= 1 works (default min(G * C, 64)).
     warmup: run one frame through every restorer before the clock starts (counted as set-up)."""
