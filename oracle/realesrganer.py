@@ -137,5 +137,8 @@ class RealESRGANer:
         output_img = np.transpose(output_img[[2, 1, 0], :, :], (1, 2, 0))
         output = (output_img * 255.0).round().astype(np.uint8)
         if outscale is not None and outscale != float(self.scale):
-            raise NotImplementedError("outscale != scale (Lanczos resize) is out of scope, SURVEY 8(f) N3")
+            import cv2  # upstream's own last step: cv2.resize(..., interpolation=cv2.INTER_LANCZOS4) on the uint8 result
+
+            h_in, w_in = img.shape[:2]
+            output = cv2.resize(output, (int(w_in * outscale), int(h_in * outscale)), interpolation=cv2.INTER_LANCZOS4)
         return output, img_mode

@@ -273,8 +273,13 @@ def test_realesrganer_signature(gpu_lib):
     ref, _ = ORef(4, oracle_model_from_sd(name, sd), tile=32, tile_pad=10, pre_pad=0).enhance(f, outscale=4)
     assert mode == "RGB"
     _check(out, ref)
-    with pytest.raises(NotImplementedError):
-        up.enhance(f, outscale=2)
+    # outscale != scale: upstream's last step, a Lanczos resize of the network-scale result with the same OpenCV call
+    import cv2
+    half, _ = up.enhance(f, outscale=2)
+    assert half.shape == (80, 100, 3)
+    assert np.array_equal(half, cv2.resize(out, (100, 80), interpolation=cv2.INTER_LANCZOS4))
+    odd, _ = up.enhance(f, outscale=2.5)
+    assert odd.shape == (100, 125, 3)
     with pytest.raises(ValueError):
         RealESRGANer(scale=2, model=name, state_dict=sd)
 

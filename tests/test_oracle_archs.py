@@ -59,6 +59,13 @@ def test_output_shapes_and_x2_modpad():
     for name in ("RealESRGAN_x4_v3", "RealESRGAN_x4plus_anime_6B"):
         out, mode = RealESRGANer(4, build_model(name, 0), tile=16, tile_pad=2, pre_pad=0).enhance(f, outscale=4)
         assert out.shape == (68, 52, 3) and out.dtype == np.uint8 and mode == "RGB"
+    # outscale != scale: Lanczos resize of the network-scale result (upstream's last step)
+    import cv2
+    up = RealESRGANer(4, build_model("RealESRGAN_x4_v3", 0), tile=16, tile_pad=2, pre_pad=0)
+    full, _ = up.enhance(f, outscale=4)
+    half, _ = up.enhance(f, outscale=2)
+    assert half.shape == (34, 26, 3)
+    assert np.array_equal(half, cv2.resize(full, (26, 34), interpolation=cv2.INTER_LANCZOS4))
     m2 = build_model("RealESRGAN_x2plus", 0)
     out, _ = RealESRGANer(2, m2, tile=8, tile_pad=2, pre_pad=0).enhance(f, outscale=2)  # 17x13 -> mod-pad 18x14
     assert out.shape == (34, 26, 3)

@@ -246,10 +246,16 @@ class RealESRGANer:
                                 blend=blend, gpu_id=gpu_id)
 
     def enhance(self, img, outscale=None, alpha_upsampler="realesrgan"):
+        """uint8 HxWx3 BGR -> (uint8 BGR, 'RGB') like upstream. The reference always passes outscale == scale
+        (video_upscaler.py:501,718); any other outscale is upstream's final step, a Lanczos resize of the network-scale
+        result on the host with the very same OpenCV call."""
+        out = self._r.process_frame(img)
         if outscale is not None and float(outscale) != float(self.scale):
-            raise NotImplementedError("outscale != scale (Lanczos resize) is out of scope; the reference always "
-                                      "passes outscale == scale (video_upscaler.py:501,718)")
-        return self._r.process_frame(img), "RGB"
+            import cv2
+
+            h, w = img.shape[:2]
+            out = cv2.resize(out, (int(w * outscale), int(h * outscale)), interpolation=cv2.INTER_LANCZOS4)
+        return out, "RGB"
 
 
 # -- stand-alone filters (host arrays) ------------------------------------------------------------
