@@ -599,11 +599,8 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
         cudaError_t pe = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         std::fprintf(stderr, "[vrb200] VR_L2PERSIST: max %d MB, set %zu MB (%s)\n", max_persist >> 20, want >> 20, cudaGetErrorString(pe));
     }
-    if (const char* e = std::getenv("VR_PDL")) h->dev.use_pdl = std::atoi(e) != 0;
-    if (const char* e = std::getenv("VR_ROLL")) h->dev.rolling = std::atoi(e);
+    read_conv_env(h->dev);
     if (const char* e = std::getenv("VR_PLANAR")) h->dev.planar = std::atoi(e) != 0;
-    if (const char* e = std::getenv("VR_PAIRPAD")) h->dev.pair_pad = std::atoi(e) != 0;
-    if (const char* e = std::getenv("VR_WRES")) h->dev.weights_resident = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);

@@ -301,17 +301,11 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     using T = PairTraits<N>;
     if (!w.wpair || w.cout != N) return 1;
     const int w_bytes = w.nchunks * T::kBHalf;
-    {
-        static const int env_direct = []() {
-            const char* e = std::getenv("VR_EPI_DIRECT");
-            return e ? std::atoi(e) : 1;
-        }();
-        // the direct epilogue needs 32-byte aligned 64-byte channel groups per pixel: chunk-planar tensors, or interleaved ones
-        // with 32-channel multiples
-        a.epi_direct = env_direct && a.omul == 1 && a.out_cstride % 32 == 0 && a.out_coff % 32 == 0 &&
-                       (!a.res1 || (a.res1_cstride % 32 == 0 && a.res1_coff % 32 == 0)) &&
-                       (!a.res2 || (a.res2_cstride % 32 == 0 && a.res2_coff % 32 == 0));
-    }
+    // the direct epilogue needs 32-byte aligned 64-byte channel groups per pixel: chunk-planar tensors, or interleaved ones with
+    // 32-channel multiples
+    a.epi_direct = dev.epi_direct && a.omul == 1 && a.out_cstride % 32 == 0 && a.out_coff % 32 == 0 &&
+                   (!a.res1 || (a.res1_cstride % 32 == 0 && a.res1_coff % 32 == 0)) &&
+                   (!a.res2 || (a.res2_cstride % 32 == 0 && a.res2_coff % 32 == 0));
     // the direct epilogue has no staging buffer: its shared memory goes to activation slots
     const int stg_bytes = a.epi_direct ? 0 : T::kStgBytes;
     int nslots = (T::kBudget + T::kStgBytes - stg_bytes - w_bytes) / T::kASlot;
@@ -331,29 +325,12 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     a.nsplit = 1;
     a.wpack = w.wpair;
     a.nstages = nslots;
-    {
-        static const int env_hint = []() {
-            const char* e = std::getenv("VR_L2HINT");
-            return e ? std::atoi(e) : 0;
-        }();
-        a.l2_hint = env_hint;
-        static const float env_frac = []() {
-            const char* e = std::getenv("VR_L2FRAC");
-            return e ? static_cast<float>(std::atof(e)) : 0.5f;
-        }();
-        a.l2_frac = env_frac;
-        static const int env_early = []() {
-            const char* e = std::getenv("VR_EARLY64");
-            return e ? std::atoi(e) : 2;
-        }();
-        a.early64 = env_early;
-    }
+    a.l2_hint = dev.l2_hint;
+    a.l2_frac = dev.l2_frac;
+    a.early64 = dev.early64;
     {
         // boxes per issuer hand-over: the next unit's operands should be landing while the current one executes
-        static const int env_unit = []() {
-            const char* e = std::getenv("VR_UNIT");
-            return e ? std::atoi(e) : 0;
-        }();
+        const int env_unit = dev.pair_unit;
         // 32 channels: up to three boxes (measured: 1 -> 2 boxes -7 %, 2 -> 3 within noise). 64 channels: the ring has only
         // six logical positions, a row pair re-uses the positions of the row pair two before it, so a unit must never hold
         // both (deadlock) and should not wait on rows the other warp is still producing: two boxes, one for single-chunk layers.
@@ -383,6 +360,25 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
     dev.launches++;
     return 0;
+}
+
+void read_conv_env(Device& dev) {
+    auto geti = [](const char* name, int* dst) {
+        if (const char* e = std::getenv(name)) *dst = std::atoi(e);
+    };
+    auto getb = [](const char* name, bool* dst) {
+        if (const char* e = std::getenv(name)) *dst = std::atoi(e) != 0;
+    };
+    getb("VR_PDL", &dev.use_pdl);
+    geti("VR_ROLL", &dev.rolling);
+    getb("VR_WRES", &dev.weights_resident);
+    getb("VR_PAIRPAD", &dev.pair_pad);
+    geti("VR_MAX_CTAS", &dev.max_ctas);
+    geti("VR_EPI_DIRECT", &dev.epi_direct);
+    geti("VR_EARLY64", &dev.early64);
+    geti("VR_UNIT", &dev.pair_unit);
+    geti("VR_L2HINT", &dev.l2_hint);
+    if (const char* e = std::getenv("VR_L2FRAC")) dev.l2_frac = static_cast<float>(std::atof(e));
 }
 
 int run_conv(Device& dev, const ConvCall& c) {

@@ -37,10 +37,7 @@ struct ScopedDev {
             return;
         }
         dev.sm_count = p.multiProcessorCount;
-        if (const char* e = std::getenv("VR_WRES")) dev.weights_resident = std::atoi(e) != 0;
-        if (const char* e = std::getenv("VR_PDL")) dev.use_pdl = std::atoi(e) != 0;
-        if (const char* e = std::getenv("VR_ROLL")) dev.rolling = std::atoi(e);
-        if (const char* e = std::getenv("VR_MAX_CTAS")) dev.max_ctas = std::atoi(e);
+        read_conv_env(dev);
         if (cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking) != cudaSuccess) {
             set_error(&err, "cudaStreamCreate failed");
             return;

@@ -102,6 +102,14 @@ struct Device {
     bool pair_pad = false;  // VR_PAIRPAD=1: K3 pairs adjacent strips only (odd strip counts get a padding strip), for A/B runs
     int max_ctas = 0;     // test hook (VR_MAX_CTAS): cap K2 / K3 grids so that a CTA / CTA pair walks several work items
     bool use_pdl = true;  // VR_PDL=0 disables programmatic dependent launch of the conv kernels
+    // K3 switches (A/B runs; defaults are the fast path): VR_EPI_DIRECT=0 stages the epilogue through shared memory;
+    // VR_EARLY64 = 0 / 1 / 2 when a 64-channel row's ring position goes back (ConvArgs::early64); VR_UNIT boxes per issuer
+    // hand-over (0 = automatic); VR_L2HINT / VR_L2FRAC cache-policy experiments (ConvArgs::l2_hint)
+    int epi_direct = 1;
+    int early64 = 2;
+    int pair_unit = 0;
+    int l2_hint = 0;
+    float l2_frac = 0.5f;
     // tensor-map cache: (ptr, cstride, W, H, rows, kc, planes, pstride)
     std::map<std::tuple<const void*, int, int, int, int, int, int, long long>, CUtensorMap> tmaps;
 };
@@ -110,6 +118,9 @@ int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const
                       ConvWeights* out, int kc = 0);  // kc = 0: default (env VR_KC or 32)
 void free_conv_weights(ConvWeights* w);
 int run_conv(Device& dev, const ConvCall& c);
+// reads every conv-related environment switch into `dev` (called when a handle / test device is created, so that one
+// process can run several configurations)
+void read_conv_env(Device& dev);
 
 // ---- elementwise / filter kernels (kernels_frame.cu) ----
 int launch_upsample2x(Device& dev, const __half* src, int H, int W, int C, __half* dst);
