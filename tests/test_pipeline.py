@@ -164,12 +164,12 @@ def test_reassembler_blocks_and_orders():
 def test_worker_error_propagates_and_does_not_hang():
     class Boom(StubRestorer):
         def process_stream(self, frames, opts):
-            for i, f in enumerate(frames):
+            for i, out in enumerate(super().process_stream(frames, opts)):
                 if self.gpu_id == 1 and i == 1:
                     raise RuntimeError("boom")
-                yield self._up(f)
+                yield out
 
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError, match="boom"):
         run_pipeline(ArraySource(clip(20)), NullSink(), lambda g: Boom(g), [0, 1], FrameOpts(temporal=True), chunk=3,
                      temporal_blend=stub_blend)
 
