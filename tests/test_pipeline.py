@@ -238,6 +238,13 @@ def test_video_file_source_and_sink_roundtrip(tmp_path):
     assert all(b > a for a, b in zip(means, means[1:])), "frames must come out in source order"
     with pytest.raises(OSError):
         VideoFileSource(str(tmp_path / "missing.mp4"))
+    # both ways of reaching a chunk's first frame deliver the same frames
+    a = list(VideoFileSource(str(src_path), seek="set").reader().read_range(5, 8))
+    rd = VideoFileSource(str(src_path), seek="grab").reader()
+    b = list(rd.read_range(5, 8))
+    assert len(a) == len(b) == 3 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    c = list(rd.read_range(2, 4))  # going back re-opens the file
+    assert len(c) == 2 and np.array_equal(c[0], list(VideoFileSource(str(src_path)).reader().read_range(2, 3))[0])
 
 
 @pytest.mark.gpu

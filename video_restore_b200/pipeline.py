@@ -86,12 +86,17 @@ class ArraySource:
 
 class VideoFileSource:
     """OpenCV-decoded video file (stands in for the reference's ffmpeg rawvideo pipe, :220-249). Every worker thread
-    gets its own `cv2.VideoCapture` (`reader()`), seeks to its chunk and decodes sequentially from there."""
+    gets its own `cv2.VideoCapture` (`reader()`) and decodes its chunks sequentially. Getting to the start of a chunk:
+    seek="set" uses CAP_PROP_POS_FRAMES (fast; exact for intra-coded and most indexed containers, but OpenCV's backends
+    may land on a neighbouring frame in some inter-coded streams); seek="grab" never seeks -- it skips forward with
+    grab() from wherever the reader is (always exact, costs the decode of the skipped frames)."""
 
-    def __init__(self, path: str):
+    def __init__(self, path: str, seek: str = "set"):
         import cv2
 
-        self.path = str(path)
+        if seek not in ("set", "grab"):
+            raise ValueError("seek must be 'set' or 'grab'")
+        self.path, self.seek = str(path), seek
         cap = cv2.VideoCapture(self.path)
         if not cap.isOpened():
             raise OSError(f"cannot open {self.path}")
@@ -105,21 +110,32 @@ class VideoFileSource:
         return self.n
 
     def reader(self) -> "_VideoReader":
-        return _VideoReader(self.path)
+        return _VideoReader(self.path, self.seek)
 
 
 class _VideoReader:
-    def __init__(self, path: str):
+    def __init__(self, path: str, seek: str = "set"):
         import cv2
 
         self._cv2 = cv2
+        self.path, self.seek = path, seek
         self.cap = cv2.VideoCapture(path)
         self.pos = 0
 
     def read_range(self, start: int, end: int):
         if self.pos != start:
-            self.cap.set(self._cv2.CAP_PROP_POS_FRAMES, start)
-            self.pos = start
+            if self.seek == "set":
+                self.cap.set(self._cv2.CAP_PROP_POS_FRAMES, start)
+                self.pos = start
+            else:
+                if self.pos > start:  # chunks come in increasing order per worker; re-open if a caller goes back
+                    self.cap.release()
+                    self.cap = self._cv2.VideoCapture(self.path)
+                    self.pos = 0
+                while self.pos < start:
+                    if not self.cap.grab():
+                        return
+                    self.pos += 1
         for _ in range(start, end):
             ok, frame = self.cap.read()
             if not ok:
