@@ -112,6 +112,11 @@ int vr_temporal_set_prev(vr_handle* h, const uint8_t* up_prev, int32_t sH, int32
                          int32_t is_device);
 int vr_temporal_get_prev(vr_handle* h, uint8_t* dst, int32_t sH, int32_t sW, int64_t stride, int32_t is_device);
 
+/* Temporal blend of two DEVICE frames on the handle's stream (asynchronous): a frame-range shard finishes its head frame
+ * with it once the left neighbour's last un-blended frame has arrived peer-to-peer. alpha / tau <= 0: defaults 0.2 / 12. */
+int vr_temporal_device(vr_handle* h, const uint8_t* d_cur, const uint8_t* d_prev, int32_t sH, int32_t sW, uint8_t* d_out,
+                       float alpha, float tau);
+
 /* ---- integer tile geometry (RealESRGANer.tile_process index arithmetic), bit-exact contract ----
  * Writes up to max_tiles rows of 12 int32:
  *   {in_x0,in_x1,in_y0,in_y1, pad_x0,pad_x1,pad_y0,pad_y1, out_x0,out_x1,out_y0,out_y1}
@@ -166,10 +171,20 @@ int64_t vr_last_conv_cycles(void);
  * tiles), 6 pre (u8 -> fp16 NHWC32), 7 nearest x2 upsample (64 channels). */
 int vr_filter_bench(int32_t device, int32_t kind, int32_t H, int32_t W, int32_t iters, float* ms_out);
 
+/* Feature-level parity hook: an intermediate tensor of the LAST restored frame as fp32 [Ha][Wa][64] over the tile atlas
+ * (single tile: the padded tile). RRDBNet: "feat" (conv_first), "body" (last RRDB's output), "trunk" (feat + conv_body(body));
+ * SRVGG: "body" (input of the last conv). out may be NULL to query the extents. capacity in floats. */
+int vr_debug_activation(vr_handle* h, const char* which, float* out, int64_t capacity, int32_t* Ha, int32_t* Wa,
+                        int32_t* C);
+
 /* Counters since handle creation: kernels launched by this library, for bench.py's gpu_launches. */
 int64_t vr_launch_count(const vr_handle* h);
-/* Average device ms of the conv kernels / all kernels in the last vr_restore* call (CUDA events on the stream). */
+int64_t vr_conv_launch_count(const vr_handle* h); /* of which convolution kernels */
+/* Device ms per frame of the whole chain / of the network (conv kernels), averaged over the frames enqueued since the
+ * previous vr_sync (CUDA events on the handle's stream, one record per frame, the last 256 at most);
+ * vr_last_timing_frames = how many frames that average covers. */
 int vr_last_timing(const vr_handle* h, float* total_ms, float* conv_ms);
+int32_t vr_last_timing_frames(const vr_handle* h);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,92 @@
+"""fp16-STORAGE emulation of the two networks on the CPU: the precision model of the reference's `half=True` GPU path
+(video_upscaler.py:335,714) as the B200 kernels implement it.
+
+TEST INFRASTRUCTURE -- see oracle/__init__.py. The fp32 oracle (oracle/archs.py) defines the tolerance target of the north
+star (+-1 LSB, PSNR >= 50 dB); this file is the SENSITIVE comparator next to it: weights rounded to fp16, every STORED
+activation rounded to fp16 once, all arithmetic in between (convolution sums, bias, LeakyReLU / PReLU, the x0.2 residual
+epilogues) in fp32 -- exactly the points at which the CUDA path rounds. Against this model the CUDA features differ only by
+fp32 summation order (and the rare fp16 rounding such a difference flips), i.e. ~1e-4 relative instead of the ~1e-3 that
+separates fp16 storage from fp32, so a wrong layer deep in the body cannot hide under the residual scalings
+("a network-level parity test that is sensitive to the body"; SURVEY.md section 7 "amplified-weight model").
+
+Parity status: follows oracle/archs.py (unpinned upstream restatement, see there); nothing here is product code.
+"""
+from __future__ import annotations
+
+import torch
+from torch.nn import functional as F
+
+from .archs import RRDBNet, SRVGGNetCompact, pixel_unshuffle
+
+
+def _h(t: torch.Tensor) -> torch.Tensor:
+    return t.half().float()
+
+
+def _conv(x, conv):
+    return F.conv2d(x, _h(conv.weight), conv.bias, padding=1)
+
+
+def _rdb(b, x):
+    lr = lambda t: F.leaky_relu(t, 0.2)
+    x1 = _h(lr(_conv(x, b.conv1)))
+    x2 = _h(lr(_conv(torch.cat((x, x1), 1), b.conv2)))
+    x3 = _h(lr(_conv(torch.cat((x, x1, x2), 1), b.conv3)))
+    x4 = _h(lr(_conv(torch.cat((x, x1, x2, x3), 1), b.conv4)))
+    return _conv(torch.cat((x, x1, x2, x3, x4), 1), b.conv5)  # fp32: the caller fuses the residual before rounding
+
+
+@torch.no_grad()
+def rrdbnet_fp16_storage(m: RRDBNet, x: torch.Tensor, features: dict | None = None) -> torch.Tensor:
+    """x: fp32 [1,3,H,W] in [0,1] (RGB). Returns the fp32 network output; `features` (optional dict) receives
+    'feat', 'body', 'trunk' as [H,W,64] fp32 arrays (what vr_debug_activation returns)."""
+    x = _h(x)
+    if m.scale == 2:
+        x = pixel_unshuffle(x, 2)
+    elif m.scale == 1:
+        x = pixel_unshuffle(x, 4)
+    feat = _h(_conv(x, m.conv_first))
+    cur = feat
+    for blk in m.body:
+        a = _h(_rdb(blk.rdb1, cur) * 0.2 + cur)
+        b = _h(_rdb(blk.rdb2, a) * 0.2 + a)
+        cur = _h((_rdb(blk.rdb3, b) * 0.2 + b) * 0.2 + cur)  # both skips in one fp32 epilogue, one rounding
+    trunk = _h(_conv(cur, m.conv_body) + feat)
+    if features is not None:
+        for k, v in (("feat", feat), ("body", cur), ("trunk", trunk)):
+            features[k] = v[0].permute(1, 2, 0).contiguous().numpy()
+    lr = lambda t: F.leaky_relu(t, 0.2)
+    f = _h(lr(_conv(F.interpolate(trunk, scale_factor=2, mode="nearest"), m.conv_up1)))
+    f = _h(lr(_conv(F.interpolate(f, scale_factor=2, mode="nearest"), m.conv_up2)))
+    f = _h(lr(_conv(f, m.conv_hr)))
+    return _h(_conv(f, m.conv_last))
+
+
+@torch.no_grad()
+def srvgg_fp16_storage(m: SRVGGNetCompact, x: torch.Tensor, features: dict | None = None) -> torch.Tensor:
+    x = _h(x)
+    out = x
+    n = len(m.body)
+    for i in range(0, n - 1, 2):
+        out = _h(F.prelu(_conv(out, m.body[i]), m.body[i + 1].weight))
+    if features is not None:
+        features["body"] = out[0].permute(1, 2, 0).contiguous().numpy()
+    out = F.pixel_shuffle(_conv(out, m.body[n - 1]), m.upscale)
+    return _h(out + F.interpolate(x, scale_factor=m.upscale, mode="nearest"))
+
+
+def forward_fp16_storage(m, x, features=None):
+    if isinstance(m, RRDBNet):
+        return rrdbnet_fp16_storage(m, x, features)
+    return srvgg_fp16_storage(m, x, features)
+
+
+@torch.no_grad()
+def rrdbnet_features_fp32(m: RRDBNet, x: torch.Tensor) -> dict:
+    """'feat', 'body', 'trunk' of the fp32 oracle, [H,W,64] arrays."""
+    if m.scale == 2:
+        x = pixel_unshuffle(x, 2)
+    feat = m.conv_first(x)
+    body = m.body(feat)
+    trunk = feat + m.conv_body(body)
+    return {k: v[0].permute(1, 2, 0).contiguous().numpy() for k, v in (("feat", feat), ("body", body), ("trunk", trunk))}

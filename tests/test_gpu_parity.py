@@ -15,7 +15,9 @@ G = Path(__file__).resolve().parent / "golden"
 
 LSB_TOL = 1          # uint8 levels
 PSNR_TOL = 50.0      # dB
-CONV_ATOL, CONV_RTOL = 2e-2, 4e-3   # single conv, fp16 storage vs fp32 reference of fp16-rounded operands
+# single conv: fp16-rounded operands, fp32 accumulation, ONE fp16 rounding of the result (half an ulp = 4.9e-4 relative);
+# 2e-3 + 2e-3 |ref| is four half-ulps (round 1 allowed 2e-2: ~40)
+CONV_ATOL, CONV_RTOL = 2e-3, 2e-3
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -369,8 +371,8 @@ def test_full_size_480p_srvgg_crop_property(gpu_lib):
 
 
 def test_full_size_720p_x4plus_runs_and_is_tile_consistent(gpu_lib):
-    """BASELINE configs[3] size. The oracle needs ~1 min/frame here, so parity at this size is checked through
-    properties: determinism, and crop-merge tiling vs single tile differing by <= 1 LSB on < 4 % of pixels
+    """BASELINE configs[3] size, properties only (the oracle comparison over the whole frame at this size is
+    tests/test_gpu_fullsize.py): determinism, and crop-merge tiling vs single tile differing by <= 1 LSB on < 4 % of pixels
     (tile borders only matter through zero padding 10+ px away; K2 / K3 sum an output row's taps in an
     order that depends on the row's parity inside its band (and, in K3, on its ring position), so identical tile interiors
     can round differently in fp16: 0.5 % with K1 only, 1.2 % with K2 on the 32-channel layers, 2.4 % with K3 everywhere)."""

@@ -67,8 +67,14 @@ def _worker(rank, world, port, out_dir, defer_head=False):
     inner = orc.upscale_only
     orc.upscale_only = lambda f, o: (calls.__setitem__(0, calls[0] + 1), inner(f, o))[1]
     from oracle import filters as OF
-    n = sh.run(orc, lambda i: frames[i], lambda i, o: results.__setitem__(i, o), _opts(), defer_head=defer_head,
-               temporal_blend=OF.temporal_blend)
+    if defer_head == "stream":
+        # the pipelined host path of the product restorer (process_stream), stood in for by a generator over the oracle
+        orc.process_stream = lambda fs, o: (orc.process_frame(f, o) for f in fs)
+        n = sh.run_stream(orc, lambda i: frames[i], lambda i, o: results.__setitem__(i, o.copy()), _opts(),
+                          temporal_blend=OF.temporal_blend)
+    else:
+        n = sh.run(orc, lambda i: frames[i], lambda i, o: results.__setitem__(i, o), _opts(), defer_head=defer_head,
+                   temporal_blend=OF.temporal_blend)
     assert n == len(results)
     # the boundary protocol of step 1 costs one extra upscale per sending rank; the deferred head costs none
     assert calls[0] == n + (0 if defer_head or rank == world - 1 else 1)
@@ -77,7 +83,7 @@ def _worker(rank, world, port, out_dir, defer_head=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,defer_head", [(2, False), (2, True), (3, True)])
+@pytest.mark.parametrize("world,defer_head", [(2, False), (2, True), (3, True), (3, "stream")])
 def test_two_shards_equal_one_shard(tmp_path, world, defer_head):
     torch.set_num_threads(2)
     frames = _frames()

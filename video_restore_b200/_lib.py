@@ -85,8 +85,14 @@ SIGNATURES = {
     "vr_conv3x3_bench": (C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_float)]),
     "vr_last_conv_cycles": (C.c_int64, []),
     "vr_filter_bench": (C.c_int, [C.c_int32] * 5 + [C.POINTER(C.c_float)]),
+    "vr_debug_activation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vr_launch_count": (C.c_int64, [C.c_void_p]),
+    "vr_conv_launch_count": (C.c_int64, [C.c_void_p]),
     "vr_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "vr_last_timing_frames": (C.c_int32, [C.c_void_p]),
+    "vr_temporal_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
+                                     C.c_float]),
 }
 
 _lib = None

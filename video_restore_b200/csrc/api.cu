@@ -91,10 +91,16 @@ struct vr_handle {
     DevBuf pipe_in[2], pipe_out[2];
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     int64_t submitted = 0;
-    cudaEvent_t ev_total[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> ev_net;
-    size_t ev_used = 0;
+    // per-frame timing events: a ring of records so that vr_sync can average over EVERY frame enqueued since the previous
+    // sync (bench.py reads the conv time of the timed steps themselves, not of one extra step)
+    struct FrameEv {
+        cudaEvent_t t0 = nullptr, c0 = nullptr, c1 = nullptr, t1 = nullptr;
+    };
+    std::vector<FrameEv> ev_ring;
+    int64_t ev_next = 0, ev_pending = 0;
+    FrameEv* ev_cur = nullptr;
     float last_total_ms = 0.f, last_conv_ms = 0.f;
+    int32_t last_frames = 0;
     bool timing_valid = false;
 };
 
@@ -349,13 +355,21 @@ int run_srvgg(vr_handle* h, int nh, int nw, __half* tile_out) {
     return 0;
 }
 
-cudaEvent_t next_event(vr_handle* h) {
-    if (h->ev_used == h->ev_net.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        h->ev_net.push_back(e);
+constexpr int kEvRing = 256;
+vr_handle::FrameEv* begin_frame_events(vr_handle* h) {
+    if (h->ev_ring.empty()) {
+        h->ev_ring.resize(kEvRing);
+        for (auto& f : h->ev_ring) {
+            cudaEventCreate(&f.t0);
+            cudaEventCreate(&f.c0);
+            cudaEventCreate(&f.c1);
+            cudaEventCreate(&f.t1);
+        }
     }
-    return h->ev_net[h->ev_used++];
+    vr_handle::FrameEv* f = &h->ev_ring[h->ev_next % kEvRing];
+    ++h->ev_next;
+    if (h->ev_pending < kEvRing) ++h->ev_pending;
+    return f;
 }
 
 // The whole per-frame chain on device-resident frames; enqueues on h->dev.stream, no host sync on the way
@@ -372,8 +386,8 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
     const int sH = H * s, sW = W * s;
     Device& dev = h->dev;
     VR_CUDA_CHECK(cudaSetDevice(dev.ordinal), dev.err);
-    h->ev_used = 0;
-    cudaEventRecord(h->ev_total[0], dev.stream);
+    vr_handle::FrameEv* fev = begin_frame_events(h);
+    cudaEventRecord(fev->t0, dev.stream);
 
     // (1) bilateral pre-denoise on the LR frame (video_upscaler.py:495-496)
     const uint8_t* src = d_bgr;
@@ -454,12 +468,12 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
     }
     h->gaps = gaps;
     h->gap_shift = 0;
-    cudaEventRecord(next_event(h), dev.stream);
+    cudaEventRecord(fev->c0, dev.stream);
     if (cfg.model_kind == VR_MODEL_RRDBNET)
         VR_TRY(run_rrdbnet(h, Ha, Wa, static_cast<__half*>(tob.p)));
     else
         VR_TRY(run_srvgg(h, Ha, Wa, static_cast<__half*>(tob.p)));
-    cudaEventRecord(next_event(h), dev.stream);
+    cudaEventRecord(fev->c1, dev.stream);
     std::vector<BlendTile> btiles;
     for (size_t ti = 0; ti < grid.size(); ++ti) {
         const TileRect& t = grid[ti];
@@ -529,22 +543,33 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
             h->prev_w = sW;
         }
     }
-    cudaEventRecord(h->ev_total[1], dev.stream);
+    cudaEventRecord(fev->t1, dev.stream);
     h->timing_valid = false;
     return 0;
 }
 
 int finish_timing(vr_handle* h) {
     VR_CUDA_CHECK(cudaStreamSynchronize(h->dev.stream), h->dev.err);
-    cudaEventElapsedTime(&h->last_total_ms, h->ev_total[0], h->ev_total[1]);
-    float conv = 0.f;
-    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev_net[i], h->ev_net[i + 1]);
-        conv += ms;
+    // average over the frames enqueued since the previous sync (at most the ring's depth; a frame whose enqueue failed half
+    // way has unrecorded events and is skipped)
+    double total = 0.0, conv = 0.0;
+    int n = 0;
+    for (int64_t i = h->ev_next - h->ev_pending; i < h->ev_next; ++i) {
+        const vr_handle::FrameEv& f = h->ev_ring[i % kEvRing];
+        float t = 0.f, c = 0.f;
+        if (cudaEventElapsedTime(&t, f.t0, f.t1) != cudaSuccess || cudaEventElapsedTime(&c, f.c0, f.c1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        total += t;
+        conv += c;
+        ++n;
     }
-    h->last_conv_ms = conv;
-    h->timing_valid = true;
+    h->ev_pending = 0;
+    h->last_frames = n;
+    h->last_total_ms = n ? static_cast<float>(total / n) : 0.f;
+    h->last_conv_ms = n ? static_cast<float>(conv / n) : 0.f;
+    h->timing_valid = n > 0;
     return 0;
 }
 
@@ -606,8 +631,6 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->dev.stream, cudaStreamNonBlocking) != cudaSuccess)
         return bad("cudaStreamCreate failed", VR_E_CUDA);
-    cudaEventCreate(&h->ev_total[0]);
-    cudaEventCreate(&h->ev_total[1]);
     *out = h.release();
     return VR_OK;
 }
@@ -633,9 +656,12 @@ void vr_destroy(vr_handle* h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->dev.dep_buf) cudaFree(h->dev.dep_buf);
-    for (auto e : h->ev_net) cudaEventDestroy(e);
-    if (h->ev_total[0]) cudaEventDestroy(h->ev_total[0]);
-    if (h->ev_total[1]) cudaEventDestroy(h->ev_total[1]);
+    for (auto& f : h->ev_ring) {
+        cudaEventDestroy(f.t0);
+        cudaEventDestroy(f.c0);
+        cudaEventDestroy(f.c1);
+        cudaEventDestroy(f.t1);
+    }
     if (h->dev.stream) cudaStreamDestroy(h->dev.stream);
     delete h;
 }
@@ -870,12 +896,68 @@ int vr_tile_grid(int32_t H, int32_t W, int32_t tile, int32_t tile_pad, int32_t s
 }
 
 int64_t vr_launch_count(const vr_handle* h) { return h ? h->dev.launches : 0; }
+int64_t vr_conv_launch_count(const vr_handle* h) { return h ? h->dev.conv_launches : 0; }
+
+// Test hook: one of the network's intermediate feature tensors of the LAST restored frame, as fp32 [Ha][Wa][64] over the
+// whole tile atlas (a single-tile frame's atlas is the padded tile itself). RRDBNet: "feat" = conv_first output, "body" =
+// output of the last RRDB (x slot of the first dense-block buffer), "trunk" = feat + conv_body(body). SRVGG: "body" = input
+// of the last conv. Feature-level parity needs this: with default-init weights 345 of x4plus's 351 convs barely move the
+// 8-bit frame, so a wrong layer deep in the body would hide under the two x0.2 residual scalings.
+int vr_debug_activation(vr_handle* h, const char* which, float* out, int64_t capacity, int32_t* Ha, int32_t* Wa, int32_t* C) {
+    if (!h || !which) return VR_E_INVALID;
+    if (h->atlas_h <= 0 || h->atlas_w <= 0) return fail(h, VR_E_STATE, "vr_debug_activation: no frame has been restored yet");
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    const std::string w(which);
+    const DevBuf* b = nullptr;
+    if (h->cfg.model_kind == VR_MODEL_RRDBNET) {
+        if (w == "feat") b = &h->feat;
+        else if (w == "body") b = &h->rdb[0];
+        else if (w == "trunk") b = &h->trunk;
+    } else if (w == "body") {
+        b = &h->sv[h->cfg.num_conv & 1];  // body.0 writes sv[0]; every body conv swaps the two buffers
+    }
+    if (!b || !b->p) return fail(h, VR_E_INVALID, "vr_debug_activation: unknown tensor '" + w + "'");
+    const size_t px = static_cast<size_t>(h->atlas_h) * h->atlas_w;
+    if (Ha) *Ha = h->atlas_h;
+    if (Wa) *Wa = h->atlas_w;
+    if (C) *C = 64;
+    if (!out) return VR_OK;
+    if (capacity < static_cast<int64_t>(px * 64)) return fail(h, VR_E_INVALID, "vr_debug_activation: output buffer too small");
+    VR_CUDA_CHECK(cudaStreamSynchronize(h->dev.stream), h->dev.err);
+    std::vector<__half> tmp(px * 64);
+    const bool planar = h->dev.planar;
+    if (planar) {  // two planes of 32 channels, px * 32 elements apart (the first two planes of a 6-plane dense-block buffer)
+        VR_CUDA_CHECK(cudaMemcpy(tmp.data(), b->p, px * 64 * sizeof(__half), cudaMemcpyDeviceToHost), h->dev.err);
+        for (size_t p = 0; p < px; ++p)
+            for (int c = 0; c < 64; ++c) out[p * 64 + c] = __half2float(tmp[(static_cast<size_t>(c >> 5) * px + p) * 32 + (c & 31)]);
+    } else {
+        const int cs = (b == &h->rdb[0]) ? 192 : 64;
+        std::vector<__half> t2(px * cs);
+        VR_CUDA_CHECK(cudaMemcpy(t2.data(), b->p, px * cs * sizeof(__half), cudaMemcpyDeviceToHost), h->dev.err);
+        for (size_t p = 0; p < px; ++p)
+            for (int c = 0; c < 64; ++c) out[p * 64 + c] = __half2float(t2[p * cs + c]);
+    }
+    return VR_OK;
+}
 
 int vr_last_timing(const vr_handle* h, float* total_ms, float* conv_ms) {
     if (!h || !h->timing_valid) return VR_E_STATE;
     if (total_ms) *total_ms = h->last_total_ms;
     if (conv_ms) *conv_ms = h->last_conv_ms;
     return VR_OK;
+}
+
+int32_t vr_last_timing_frames(const vr_handle* h) { return (h && h->timing_valid) ? h->last_frames : 0; }
+
+// Stand-alone temporal blend on DEVICE frames, enqueued on the handle's stream: finishes a frame-range shard's head frame
+// when the left neighbour's last un-blended frame has arrived peer-to-peer (no host staging).
+int vr_temporal_device(vr_handle* h, const uint8_t* d_cur, const uint8_t* d_prev, int32_t sH, int32_t sW, uint8_t* d_out,
+                       float alpha, float tau) {
+    if (!h) return VR_E_INVALID;
+    if (!d_cur || !d_prev || !d_out || sH <= 0 || sW <= 0) return fail(h, VR_E_INVALID, "vr_temporal_device: bad arguments");
+    VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+    const int64_t st = static_cast<int64_t>(sW) * 3;
+    return launch_temporal(h->dev, d_cur, st, d_prev, st, sH, sW, d_out, st, alpha > 0 ? alpha : 0.2f, tau > 0 ? tau : 12.f);
 }
 
 }  // extern "C"

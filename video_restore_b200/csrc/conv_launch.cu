@@ -233,6 +233,7 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     cfg.numAttrs = 1;
     VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
     dev.launches++;
+    dev.conv_launches++;
     return 0;
 }
 
@@ -292,6 +293,7 @@ static int launch_roll(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     cfg.numAttrs = 1;
     VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
     dev.launches++;
+    dev.conv_launches++;
     return 0;
 }
 
@@ -359,6 +361,7 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     cfg.numAttrs = 1;
     VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
     dev.launches++;
+    dev.conv_launches++;
     return 0;
 }
 

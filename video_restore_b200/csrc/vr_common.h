@@ -82,6 +82,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     std::string* err = nullptr;
     int64_t launches = 0;
+    int64_t conv_launches = 0;  // of which convolution kernels (K1 / K2 / K3 / K4)
     // dependency counters of multi-layer launches: two regions used alternately (each launch zeroes the other one)
     int* dep_buf = nullptr;
     int dep_parity = 0;

@@ -186,15 +186,39 @@ class FrameRestorer:
                    self._h)
         return a
 
+    def temporal_blend_device(self, d_cur: int, d_prev: int, sH: int, sW: int, d_out: int, alpha: float = 0.2,
+                              tau: float = 12.0) -> None:
+        """Temporal blend of two device frames on this restorer's stream (asynchronous; `sync()` to wait)."""
+        _lib.check(self._lib.vr_temporal_device(self._h, C.c_void_p(int(d_cur)), C.c_void_p(int(d_prev)), sH, sW,
+                                                C.c_void_p(int(d_out)), alpha, tau), self._h)
+
     # -- introspection ---------------------------------------------------------------------------
     @property
     def launch_count(self) -> int:
         return int(self._lib.vr_launch_count(self._h))
 
+    def debug_activation(self, which: str) -> np.ndarray:
+        """Test hook: fp32 [Ha, Wa, 64] intermediate tensor ("feat" / "body" / "trunk") of the last restored frame."""
+        ha, wa, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _lib.check(self._lib.vr_debug_activation(self._h, which.encode(), None, 0, C.byref(ha), C.byref(wa), C.byref(c)),
+                   self._h)
+        out = np.empty((ha.value, wa.value, c.value), np.float32)
+        _lib.check(self._lib.vr_debug_activation(self._h, which.encode(), out.ctypes.data_as(C.c_void_p), out.size,
+                                                 C.byref(ha), C.byref(wa), C.byref(c)), self._h)
+        return out
+
+    @property
+    def conv_launch_count(self) -> int:
+        return int(self._lib.vr_conv_launch_count(self._h))
+
     def last_timing(self):
         t, c = C.c_float(0), C.c_float(0)
         _lib.check(self._lib.vr_last_timing(self._h, C.byref(t), C.byref(c)), self._h)
         return float(t.value), float(c.value)
+
+    def last_timing_frames(self) -> int:
+        """Number of frames `last_timing()` averages over (frames enqueued since the previous sync)."""
+        return int(self._lib.vr_last_timing_frames(self._h))
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
