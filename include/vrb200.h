@@ -117,6 +117,15 @@ int vr_temporal_get_prev(vr_handle* h, uint8_t* dst, int32_t sH, int32_t sW, int
 int vr_temporal_device(vr_handle* h, const uint8_t* d_cur, const uint8_t* d_prev, int32_t sH, int32_t sW, uint8_t* d_out,
                        float alpha, float tau);
 
+/* Boundary frame between two handles of ONE process (one host thread + handle per GPU; replaces the shared queue of
+ * video_upscaler.py:430-488 for the temporal stage): vr_boundary_send copies src's temporal state (its last un-blended upscaled
+ * frame) into a device buffer on dst's device with ONE cudaMemcpyPeerAsync (NVLink between peers) and returns it in *d_frame;
+ * vr_boundary_finish (dst's thread) blends a host head frame with it into a host output and recycles the buffer (head == NULL:
+ * recycle only). */
+int vr_boundary_send(vr_handle* src, vr_handle* dst, int32_t sH, int32_t sW, void** d_frame);
+int vr_boundary_finish(vr_handle* h, void* d_prev, const uint8_t* head, int64_t head_stride, uint8_t* out, int64_t out_stride,
+                       int32_t sH, int32_t sW, float alpha, float tau);
+
 /* ---- integer tile geometry (RealESRGANer.tile_process index arithmetic), bit-exact contract ----
  * Writes up to max_tiles rows of 12 int32:
  *   {in_x0,in_x1,in_y0,in_y1, pad_x0,pad_x1,pad_y0,pad_y1, out_x0,out_x1,out_y0,out_y1}

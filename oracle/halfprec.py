@@ -90,3 +90,17 @@ def rrdbnet_features_fp32(m: RRDBNet, x: torch.Tensor) -> dict:
     body = m.body(feat)
     trunk = feat + m.conv_body(body)
     return {k: v[0].permute(1, 2, 0).contiguous().numpy() for k, v in (("feat", feat), ("body", body), ("trunk", trunk))}
+
+
+class HalfStorageNet:
+    """Drop-in for the nn.Module inside oracle.realesrganer.RealESRGANer: the same network evaluated with the fp16-storage
+    precision model above (what the reference's `half=True` path stores), so whole tiled frames can be produced with it."""
+
+    def __init__(self, model):
+        self.model = model.eval()
+
+    def eval(self):
+        return self
+
+    def __call__(self, x):
+        return forward_fp16_storage(self.model, x)

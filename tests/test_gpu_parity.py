@@ -244,6 +244,9 @@ def _check(out, ref):
     ("RealESRGAN_x4plus", 40, 72, 32, 8, "gaussian"),
     ("RealESRGAN_x2plus", 66, 90, 32, 8, "crop"),
     ("RealESRGAN_x2plus", 65, 91, 32, 8, "gaussian"),               # odd extent: reflect mod-pad
+    ("RealESRGAN_x4plus_anime_6B", 40, 150, 16, 4, "crop"),         # 10 tiles per row: two atlas groups (8 + 2 columns)
+    ("RealESRGAN_x4_v3", 150, 40, 16, 4, "gaussian"),               # 10 tile rows, blended across the group boundary
+    ("RealESRGAN_x2plus", 36, 280, 32, 8, "crop"),                  # 9 tile columns on the pixel-unshuffled grid
 ])
 def test_enhance_parity(gpu_lib, name, H, W, tile, pad, blend):
     gpu, orc = _pair(name, tile, pad, blend)
@@ -284,6 +287,12 @@ def test_realesrganer_signature(gpu_lib):
     assert odd.shape == (100, 125, 3)
     with pytest.raises(ValueError):
         RealESRGANer(scale=2, model=name, state_dict=sd)
+    # upstream's DEFAULT pre_pad = 10 (reflect pad bottom / right, crop afterwards); the reference passes 0 (:334)
+    up10 = RealESRGANer(scale=4, model=name, tile=32, tile_pad=10, half=True, gpu_id=0, state_dict=sd)
+    assert up10.pre_pad == 10
+    out10, _ = up10.enhance(f, outscale=4)
+    ref10, _ = ORef(4, oracle_model_from_sd(name, sd), tile=32, tile_pad=10, pre_pad=10).enhance(f, outscale=4)
+    _check(out10, ref10)
 
 
 def test_x2_odd_tile_rejected(gpu_lib):
@@ -542,5 +551,6 @@ def test_tile_grid_full_sizes(gpu_lib):
 
     for H, W, tile, pad, s in [(720, 1280, 512, 64, 4), (720, 1280, 1536, 10, 4), (1080, 1920, 512, 32, 2),
                                (1080, 1920, 1024, 10, 4), (1080, 1920, 512, 32, 4), (480, 854, 1024, 16, 4),
-                               (256, 256, 128, 16, 4), (2160, 3840, 512, 32, 4)]:
+                               (256, 256, 128, 16, 4), (2160, 3840, 512, 32, 4), (2160, 3840, 256, 10, 4),
+                               (1080, 1920, 128, 16, 4)]:
         assert np.array_equal(R.tile_grid(H, W, tile, pad, s), o_tile_grid(H, W, tile, pad, s)), (H, W, tile)

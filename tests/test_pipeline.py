@@ -247,6 +247,35 @@ def test_video_file_source_and_sink_roundtrip(tmp_path):
     assert len(c) == 2 and np.array_equal(c[0], list(VideoFileSource(str(src_path)).reader().read_range(2, 3))[0])
 
 
+def test_video_file_source_counts_exactly_and_decodes_sequentially(tmp_path):
+    """the container's frame count is a hint. The source counts frames itself (grab pass), the default reader is ONE
+    sequential decoder shared by all workers (no seeks), frames past EOF end the range, and a frame is handed out once."""
+    from video_restore_b200.pipeline import ListSink, VideoFileSource
+
+    p = tmp_path / "c.mp4"
+    _write_clip(p, 10)
+    src = VideoFileSource(str(p), lookahead=4)          # look-ahead smaller than G * chunk: must not deadlock
+    assert len(src) == 10
+    sink = ListSink()
+    st = run_pipeline(src, sink, lambda g: StubRestorer(g), [0, 1, 2], FrameOpts(temporal=True), chunk=2,
+                      temporal_blend=stub_blend)
+    assert st.frames == 10 and sink.order == list(range(10))
+    src = VideoFileSource(str(p))
+    rd = src.reader()
+    assert len(list(rd.read_range(8, 20))) == 2         # stops at EOF
+    assert len(list(rd.read_range(3, 4))) == 1          # still buffered: decoded on the way to frame 8, never taken
+    with pytest.raises(RuntimeError, match="already consumed"):
+        list(rd.read_range(3, 4))
+    assert len(list(rd.read_range(0, 1))) == 1          # frame 0 stays available (warm-up reads)
+    src.close()
+    # one long range per worker: per-worker exact readers instead of the shared decoder
+    src = VideoFileSource(str(p))
+    sink2 = ListSink()
+    run_pipeline(src, sink2, lambda g: StubRestorer(g), [0, 1], FrameOpts(temporal=True), chunk=None, temporal_blend=stub_blend)
+    assert sink2.order == list(range(10))
+    assert all(np.array_equal(a, b) for a, b in zip(sink.frames, sink2.frames))
+
+
 @pytest.mark.gpu
 def test_cli_video_file_two_workers(tmp_path, capsys):
     import cv2
@@ -256,7 +285,7 @@ def test_cli_video_file_two_workers(tmp_path, capsys):
     src_path, dst_path = tmp_path / "in.mp4", tmp_path / "out.mp4"
     _write_clip(src_path, 7)
     assert main([str(src_path), str(dst_path), "--model", "RealESRGAN_x4_v3", "--quality", "fast", "--enhanced",
-                 "--gpus", "0", "0"]) == 0
+                 "--gpus", "0", "0", "--random-weights"]) == 0
     assert "processed 7 frames" in capsys.readouterr().out
     cap = cv2.VideoCapture(str(dst_path))
     n = 0
@@ -269,7 +298,8 @@ def test_cli_video_file_two_workers(tmp_path, capsys):
     assert n == 7
     # directory mode
     out_dir = tmp_path / "outs"
-    assert main([str(tmp_path), str(out_dir), "--model", "RealESRGAN_x4_v3", "--quality", "fast", "--batch", "--gpus", "0"]) == 0
+    assert main([str(tmp_path), str(out_dir), "--model", "RealESRGAN_x4_v3", "--quality", "fast", "--batch", "--gpus", "0",
+                 "--random-weights"]) == 0
     assert (out_dir / "in_upscaled.mp4").exists()
 
 

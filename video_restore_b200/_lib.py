@@ -91,6 +91,9 @@ SIGNATURES = {
     "vr_conv_launch_count": (C.c_int64, [C.c_void_p]),
     "vr_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vr_last_timing_frames": (C.c_int32, [C.c_void_p]),
+    "vr_boundary_send": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "vr_boundary_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_float, C.c_float]),
     "vr_temporal_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
                                      C.c_float]),
 }

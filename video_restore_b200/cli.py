@@ -70,6 +70,12 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no-temporal", action="store_true")
     p.add_argument("--no-color-enhance", action="store_true")
     p.add_argument("--synthetic", type=int, default=0, help="process N synthetic 720p frames instead of a video")
+    p.add_argument("--random-weights", action="store_true",
+                   help="run with random-init weights when models/<model>.pth is absent (benchmarks / tests only: the output "
+                        "is not a restored video)")
+    p.add_argument("--procs", action="store_true",
+                   help="with several --gpus: one PROCESS per GPU over contiguous frame ranges (scales like bench.py; a video "
+                        "file is written as one segment per GPU) instead of one thread per GPU in this process")
     return p
 
 
@@ -112,32 +118,47 @@ def frame_opts_from_config(cfg: OptimizedConfig):
                      sharpen=cfg.sharpen, clahe=cfg.color_enhance, temporal=cfg.temporal)
 
 
-def make_restorer(cfg: OptimizedConfig, gpu_id: int, state_dict=None):
-    from .restorer import FrameRestorer
+class MissingWeights(FileNotFoundError):
+    pass
+
+
+def load_weights(cfg: OptimizedConfig, allow_random: bool = False):
+    """state_dict of `cfg.model_name` from the reference's cache location models/<name>.pth (video_upscaler.py:350-353).
+    The reference downloads a missing checkpoint (:342-367) or fails; there is no network here, so a missing file is an ERROR
+    unless random weights were asked for explicitly (--random-weights, implied by --synthetic)."""
+    path = Path("models") / f"{cfg.model_name}.pth"
+    if path.exists():
+        import torch
+        net = torch.load(path, map_location="cpu")
+        return net.get("params_ema", net.get("params", net))
+    if not allow_random:
+        raise MissingWeights(f"{path} not found (the reference would download it, video_upscaler.py:342-367; no network here). "
+                             f"Put the checkpoint there, or pass --random-weights to run with random-init weights "
+                             f"(benchmarks only: the output is NOT a restored video)")
     from .synth import random_state_dict
 
+    print(f"[video-restore] {path} not found: random-init weights as requested (output is not a restored video)")
+    return random_state_dict(cfg.model_name, seed=0)
+
+
+def make_restorer(cfg: OptimizedConfig, gpu_id: int, state_dict=None, allow_random: bool = False):
+    from .restorer import FrameRestorer
+
     if state_dict is None:
-        path = Path("models") / f"{cfg.model_name}.pth"  # the reference's cache location, video_upscaler.py:350-353
-        if path.exists():
-            import torch
-            net = torch.load(path, map_location="cpu")
-            state_dict = net.get("params_ema", net.get("params", net))
-        else:
-            print(f"[video-restore] {path} not found and there is no network here: using random-init weights")
-            state_dict = random_state_dict(cfg.model_name, seed=0)
+        state_dict = load_weights(cfg, allow_random)
     return FrameRestorer(cfg.model_name, state_dict, tile=cfg.tile_size, tile_pad=cfg.tile_pad,
                          blend="gaussian" if cfg.seamless else "crop", gpu_id=gpu_id)
 
 
-VIDEO_EXTS = (".mp4", ".mkv", ".avi", ".mov", ".webm", ".m4v")  # the reference's batch filter, video_upscaler.py:727-731
+VIDEO_EXTS = (".mp4", ".avi", ".mov", ".mkv", ".webm")  # the reference's batch filter, video_upscaler.py:732
 
 
-def _run_one(cfg: OptimizedConfig, opts, source, sink, chunk: int):
+def _run_one(cfg: OptimizedConfig, opts, source, sink, chunk: int, state_dict):
     """One clip through the multi-GPU pipeline (pipeline.py): one host thread + restorer per GPU in cfg.gpu_ids,
     contiguous frame chunks, one boundary frame per chunk for the temporal stage, ordered bounded reassembly."""
     from .pipeline import run_pipeline
 
-    return run_pipeline(source, sink, lambda gpu_id: make_restorer(cfg, gpu_id), cfg.gpu_ids, opts, chunk=chunk)
+    return run_pipeline(source, sink, lambda gpu_id: make_restorer(cfg, gpu_id, state_dict), cfg.gpu_ids, opts, chunk=chunk)
 
 
 def main(argv=None) -> int:
@@ -153,14 +174,31 @@ def main(argv=None) -> int:
     if not cfg.gpu_ids:
         print("Error: No CUDA GPUs available")  # same failure as video_upscaler.py:140-141
         return 1
+    try:
+        state_dict = load_weights(cfg, allow_random=args.random_weights or args.synthetic > 0)
+    except MissingWeights as e:
+        print(f"Error: {e}")
+        return 1
+    if args.procs and len(cfg.gpu_ids) > 1:
+        from .multiproc import run_processes
+
+        return run_processes(args, cfg, opts)
     # frames per contiguous range: bounds the reorder ring in front of the sequential encoder (G * 16 frames); one GPU
     # walks the clip as a single range
     chunk = 16 if len(cfg.gpu_ids) > 1 else None
     if args.synthetic > 0:
-        st = _run_one(cfg, opts, SyntheticSource(720, 1280, args.synthetic, seed=1, distinct=8), NullSink(), chunk)
+        st = _run_one(cfg, opts, SyntheticSource(720, 1280, args.synthetic, seed=1, distinct=8), NullSink(), chunk, state_dict)
         print(f"processed {st.frames} frames in {st.seconds:.2f} s ({st.fps:.2f} fps) on {len(cfg.gpu_ids)} GPU(s); "
               f"{st.boundary_frames} boundary frames exchanged; model set-up {st.setup_seconds:.1f} s")
         return 0
+    # what this build does NOT do with the reference's flags: said once, loudly, instead of silently ignoring them
+    ignored = [f for f, v in (("--crf", args.crf), ("--preset", args.preset)) if v is not None]
+    print("[video-restore] note: video is written with OpenCV ('mp4v'), not libx264"
+          + (f" -- {', '.join(ignored)} ignored" if ignored else "")
+          + ("" if args.no_audio else "; audio is NOT copied (needs the ffmpeg binary, absent here; video_upscaler.py:604-627)"))
+    if args.enhanced:
+        print("[video-restore] note: --enhanced also enables the README's seamless blend / temporal / CLAHE / unsharp stage, which "
+              "the reference's code does not implement (--no-seamless --no-temporal --no-color-enhance --sharpen 0 turn it off)")
     jobs = []
     if args.batch:  # directory mode, video_upscaler.py:723-746
         in_dir, out_dir = Path(args.input), Path(args.output)
@@ -170,18 +208,30 @@ def main(argv=None) -> int:
         out_dir.mkdir(parents=True, exist_ok=True)
         for f in sorted(in_dir.iterdir()):
             if f.suffix.lower() in VIDEO_EXTS:
-                jobs.append((f, out_dir / f"{f.stem}_upscaled.mp4"))
+                jobs.append((f, out_dir / f"{f.stem}_upscaled{f.suffix}"))  # source suffix kept, as :744
+        if not jobs:
+            print(f"No videos found in {in_dir}")
+            return 1
+        print(f"\nBatch processing {len(jobs)} videos\n")
     else:
         jobs.append((Path(args.input), Path(args.output)))
     rc = 0
     for src_path, dst_path in jobs:
+        # like process_video (:369-428): a failing clip is reported and the batch goes on
         try:
             source = VideoFileSource(str(src_path))
-        except OSError as e:
-            print(f"Error: {e}")
+            st = _run_one(cfg, opts, source, VideoFileSink(str(dst_path), source.fps), chunk, state_dict)
+        except KeyboardInterrupt:
+            print("\n\nProcessing interrupted")
+            return 1
+        except Exception as e:  # noqa: BLE001
+            print(f"Error: {src_path.name}: {e}")
             rc = 1
             continue
-        st = _run_one(cfg, opts, source, VideoFileSink(str(dst_path), source.fps), chunk)
+        if st.frames == 0:
+            print(f"Error: {src_path.name}: no frames decoded")
+            rc = 1
+            continue
         print(f"{src_path.name}: processed {st.frames} frames in {st.seconds:.2f} s ({st.fps:.2f} fps) on "
               f"{len(cfg.gpu_ids)} GPU(s)")
     return rc

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 
 using namespace vr;
 
@@ -86,6 +87,10 @@ struct vr_handle {
     int prev_h = 0, prev_w = 0;
     DevBuf clahe_hist, clahe_lut;
     BlendState blend;
+    // boundary frames received from the left neighbour's handle (in-process multi-GPU, pipeline.py): device buffers on THIS
+    // handle's device, filled by the neighbour's thread with one cudaMemcpyPeerAsync each, recycled through a free list
+    std::mutex bmu;
+    std::vector<DevBuf> bfree;
     // pipelined host path (vr_submit / vr_wait): two slots
     cudaStream_t s_in = nullptr, s_out = nullptr;
     DevBuf pipe_in[2], pipe_out[2];
@@ -174,7 +179,7 @@ void set_io(ConvCall& c, const Act& in, const Act& out) {
 
 int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act, Act res1 = Act(),
          float s1 = 1.f, Act res2 = Act(), float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr,
-         int base_c = 0, Rows rows = Rows(), int phase = -1) {
+         int base_c = 0, Rows rows = Rows(), int phase = -1, Act out2 = Act()) {
     const ConvWeights* w = layer(h, name);
     if (!w) return fail(h, VR_E_STATE, "missing layer " + name);
     ConvCall c;
@@ -185,6 +190,8 @@ int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out,
     c.act = act;
     c.slope = 0.2f;
     c.out_coff = out_coff;
+    c.out2 = out2.p;
+    c.out2_cstride = out2.ps ? 32 : out2.c;
     c.res1 = res1.p;
     c.res1_cstride = res1.ps ? 32 : res1.c;
     c.res1_pstride = res1.ps;
@@ -256,9 +263,14 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
     Act trunk = make_act(h, h->trunk.p, 64, px);
     Act rdb[3] = {make_act(h, h->rdb[0].p, 192, px), make_act(h, h->rdb[1].p, 192, px), make_act(h, h->rdb[2].p, 192, px)};
     const int band = band_rows_for(nh, nw);
-    // conv_first twice: once into `feat` (trunk residual), once into the first RDB buffer's x slot (K = 32: cheap)
-    VR_TRY(conv(h, "conv_first", in32, nh, nw, feat, 0, ACT_NONE));
-    VR_TRY(conv(h, "conv_first", in32, nh, nw, rdb[0], 0, ACT_NONE));
+    // conv_first feeds the trunk skip (`feat`) AND the first dense block's x slot: one launch, two destinations from the
+    // same epilogue registers (K3 direct epilogue); with another kernel configured (A/B switches) two launches
+    if (conv_supports_out2(h->dev, 64) && feat.ps == rdb[0].ps) {
+        VR_TRY(conv(h, "conv_first", in32, nh, nw, feat, 0, ACT_NONE, Act(), 1.f, Act(), 1.f, OUT_NHWC, nullptr, 0, Rows(), -1, rdb[0]));
+    } else {
+        VR_TRY(conv(h, "conv_first", in32, nh, nw, feat, 0, ACT_NONE));
+        VR_TRY(conv(h, "conv_first", in32, nh, nw, rdb[0], 0, ACT_NONE));
+    }
     for (int b = 0; b < h->cfg.num_block; ++b) {
         for (int r = 0; r < 3; ++r) {
             const std::string pre = "body." + std::to_string(b) + ".rdb" + std::to_string(r + 1) + ".conv";
@@ -423,71 +435,87 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
     // separated by 1-pixel zero gap columns / rows. A 3x3 conv cannot see across a zero gap that is re-zeroed after
     // every layer, and the gap is exactly the zero padding tile_process gives each tile, so the result is bit-identical
     // to running the tiles one by one -- with one launch per layer for the whole frame instead of one per tile.
-    if (tiles_x > 8 || tiles_y > 8)
-        return fail(h, VR_E_INVALID, "more than 8 tiles per axis: use a larger --tile-size");
+    // More than 8 tiles along an axis (e.g. 2160p with --tile-size 256): the grid is cut into groups of at most 8 x 8 tiles, one
+    // atlas each (the kernels' gap tables hold 7 separators per axis). RealESRGANer.tile_process has no such limit.
     const int net_div = s == 2 ? 2 : 1;  // x2 models run on the pixel-unshuffled (half resolution) grid
-    int colw[8], rowh[8], ax0[8], ay0[8];
     for (size_t ti = 0; ti < grid.size(); ++ti) {
         const TileRect& t = grid[ti];
-        const int pw = t.pad_x1 - t.pad_x0, ph = t.pad_y1 - t.pad_y0;
-        if (s == 2 && ((pw | ph) & 1))
+        if (s == 2 && (((t.pad_x1 - t.pad_x0) | (t.pad_y1 - t.pad_y0)) & 1))
             return fail(h, VR_E_INVALID,
                         "x2 model: padded tile extent must be even (pixel_unshuffle); use an even tile size/overlap");
-        colw[ti % tiles_x] = pw / net_div;
-        rowh[ti / tiles_x] = ph / net_div;
     }
-    Gaps gaps;
-    int Wa = 0, Ha = 0;
-    for (int j = 0; j < tiles_x; ++j) {
-        ax0[j] = Wa;
-        Wa += colw[j];
-        if (j + 1 < tiles_x) gaps.gx[gaps.ngx++] = Wa++;
-    }
-    for (int i = 0; i < tiles_y; ++i) {
-        ay0[i] = Ha;
-        Ha += rowh[i];
-        if (i + 1 < tiles_y) gaps.gy[gaps.ngy++] = Ha++;
-    }
-    const size_t in_bytes = static_cast<size_t>(Ha) * Wa * 32 * 2;
-    const bool in_realloc = h->in32.bytes < in_bytes || !h->in32.p;
-    VR_TRY(ensure(h, h->in32, in_bytes));
-    if (in_realloc || h->atlas_w != Wa || h->atlas_h != Ha) {
-        // gap pixels of the network input are never written by pre_kernel: zero once per layout
-        VR_CUDA_CHECK(cudaMemsetAsync(h->in32.p, 0, in_bytes, dev.stream), dev.err);
-        h->atlas_w = Wa;
-        h->atlas_h = Ha;
-    }
-    if (h->tile_out.empty()) h->tile_out.resize(1);
-    DevBuf& tob = h->tile_out[0];
-    const int out_pitch = Wa * 4;  // every model's network output is 4x the network-input grid
-    VR_TRY(ensure(h, tob, static_cast<size_t>(Ha) * 4 * out_pitch * 4 * 2));
-    for (size_t ti = 0; ti < grid.size(); ++ti) {
-        const TileRect& t = grid[ti];
-        VR_TRY(launch_pre(dev, src, sstride, H, W, t.pad_x0, t.pad_y0, t.pad_x1 - t.pad_x0, t.pad_y1 - t.pad_y0,
-                          s == 2 ? 1 : 0, static_cast<__half*>(h->in32.p), Wa, ax0[ti % tiles_x], ay0[ti / tiles_x]));
-    }
-    h->gaps = gaps;
-    h->gap_shift = 0;
-    cudaEventRecord(fev->c0, dev.stream);
-    if (cfg.model_kind == VR_MODEL_RRDBNET)
-        VR_TRY(run_rrdbnet(h, Ha, Wa, static_cast<__half*>(tob.p)));
-    else
-        VR_TRY(run_srvgg(h, Ha, Wa, static_cast<__half*>(tob.p)));
-    cudaEventRecord(fev->c1, dev.stream);
-    std::vector<BlendTile> btiles;
-    for (size_t ti = 0; ti < grid.size(); ++ti) {
-        const TileRect& t = grid[ti];
-        const int pw = t.pad_x1 - t.pad_x0, ph = t.pad_y1 - t.pad_y0;
-        const __half* origin = static_cast<const __half*>(tob.p) +
-                               (static_cast<size_t>(ay0[ti / tiles_x]) * 4 * out_pitch + ax0[ti % tiles_x] * 4) * 4;
-        if (blend) {
-            btiles.push_back({origin, t.pad_x0 * s, t.pad_y0 * s, pw * s, ph * s, out_pitch});
-        } else {
-            const int dx0 = t.in_x0 * s, dy0 = t.in_y0 * s;
-            const int w = std::min(t.in_x1 * s, sW) - dx0, hh = std::min(t.in_y1 * s, sH) - dy0;  // un-pad (post_process)
-            VR_TRY(launch_post_crop(dev, origin, out_pitch, t.out_x0, t.out_y0, w, hh, up_dst, up_stride, dx0, dy0));
+    const int groups_x = (tiles_x + 7) / 8, groups_y = (tiles_y + 7) / 8;
+    if (h->tile_out.size() < static_cast<size_t>(groups_x) * groups_y) h->tile_out.resize(static_cast<size_t>(groups_x) * groups_y);
+    std::vector<BlendTile> btiles(blend ? grid.size() : 0);
+    for (int gy = 0; gy < groups_y; ++gy)
+        for (int gx = 0; gx < groups_x; ++gx) {
+            const int tx0 = gx * 8, ty0 = gy * 8;
+            const int ntx = std::min(8, tiles_x - tx0), nty = std::min(8, tiles_y - ty0);
+            int colw[8], rowh[8], ax0[8], ay0[8];
+            for (int j = 0; j < ntx; ++j) {
+                const TileRect& t = grid[static_cast<size_t>(ty0) * tiles_x + tx0 + j];
+                colw[j] = (t.pad_x1 - t.pad_x0) / net_div;
+            }
+            for (int i = 0; i < nty; ++i) {
+                const TileRect& t = grid[static_cast<size_t>(ty0 + i) * tiles_x + tx0];
+                rowh[i] = (t.pad_y1 - t.pad_y0) / net_div;
+            }
+            Gaps gaps;
+            int Wa = 0, Ha = 0;
+            for (int j = 0; j < ntx; ++j) {
+                ax0[j] = Wa;
+                Wa += colw[j];
+                if (j + 1 < ntx) gaps.gx[gaps.ngx++] = Wa++;
+            }
+            for (int i = 0; i < nty; ++i) {
+                ay0[i] = Ha;
+                Ha += rowh[i];
+                if (i + 1 < nty) gaps.gy[gaps.ngy++] = Ha++;
+            }
+            const size_t in_bytes = static_cast<size_t>(Ha) * Wa * 32 * 2;
+            const bool in_realloc = h->in32.bytes < in_bytes || !h->in32.p;
+            VR_TRY(ensure(h, h->in32, in_bytes));
+            if (in_realloc || h->atlas_w != Wa || h->atlas_h != Ha) {
+                // gap pixels of the network input are never written by pre_kernel: zero once per layout
+                VR_CUDA_CHECK(cudaMemsetAsync(h->in32.p, 0, in_bytes, dev.stream), dev.err);
+                h->atlas_w = Wa;
+                h->atlas_h = Ha;
+            }
+            DevBuf& tob = h->tile_out[static_cast<size_t>(gy) * groups_x + gx];
+            const int out_pitch = Wa * 4;  // every model's network output is 4x the network-input grid
+            VR_TRY(ensure(h, tob, static_cast<size_t>(Ha) * 4 * out_pitch * 4 * 2));
+            for (int i = 0; i < nty; ++i)
+                for (int j = 0; j < ntx; ++j) {
+                    const TileRect& t = grid[static_cast<size_t>(ty0 + i) * tiles_x + tx0 + j];
+                    VR_TRY(launch_pre(dev, src, sstride, H, W, t.pad_x0, t.pad_y0, t.pad_x1 - t.pad_x0, t.pad_y1 - t.pad_y0,
+                                      s == 2 ? 1 : 0, static_cast<__half*>(h->in32.p), Wa, ax0[j], ay0[i]));
+                }
+            h->gaps = gaps;
+            h->gap_shift = 0;
+            // conv time of the frame: first network launch .. last network launch (with several groups the few pre / merge
+            // kernels between the groups' networks are inside the bracket: < 1 %)
+            if (gx == 0 && gy == 0) cudaEventRecord(fev->c0, dev.stream);
+            if (cfg.model_kind == VR_MODEL_RRDBNET)
+                VR_TRY(run_rrdbnet(h, Ha, Wa, static_cast<__half*>(tob.p)));
+            else
+                VR_TRY(run_srvgg(h, Ha, Wa, static_cast<__half*>(tob.p)));
+            if (gx == groups_x - 1 && gy == groups_y - 1) cudaEventRecord(fev->c1, dev.stream);
+            for (int i = 0; i < nty; ++i)
+                for (int j = 0; j < ntx; ++j) {
+                    const size_t ti = static_cast<size_t>(ty0 + i) * tiles_x + tx0 + j;
+                    const TileRect& t = grid[ti];
+                    const int pw = t.pad_x1 - t.pad_x0, ph = t.pad_y1 - t.pad_y0;
+                    const __half* origin =
+                        static_cast<const __half*>(tob.p) + (static_cast<size_t>(ay0[i]) * 4 * out_pitch + ax0[j] * 4) * 4;
+                    if (blend) {
+                        btiles[ti] = {origin, t.pad_x0 * s, t.pad_y0 * s, pw * s, ph * s, out_pitch};
+                    } else {
+                        const int dx0 = t.in_x0 * s, dy0 = t.in_y0 * s;
+                        const int w = std::min(t.in_x1 * s, sW) - dx0, hh = std::min(t.in_y1 * s, sH) - dy0;  // un-pad (post_process)
+                        VR_TRY(launch_post_crop(dev, origin, out_pitch, t.out_x0, t.out_y0, w, hh, up_dst, up_stride, dx0, dy0));
+                    }
+                }
         }
-    }
     if (blend) {
         VR_TRY(launch_post_blend(dev, btiles, tiles_x, tiles_y, cfg.tile * s, cfg.tile_pad * s, up_dst, up_stride, sH,
                                  sW, h->blend));
@@ -646,6 +674,7 @@ void vr_destroy(vr_handle* h) {
     for (DevBuf* b : bufs) release(*b);
     for (auto& b : h->tile_out) release(b);
     free_blend_state(h->blend);
+    for (auto& b : h->bfree) release(b);
     for (int i = 0; i < 2; ++i) {
         release(h->pipe_in[i]);
         release(h->pipe_out[i]);
@@ -656,6 +685,7 @@ void vr_destroy(vr_handle* h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->dev.dep_buf) cudaFree(h->dev.dep_buf);
+    if (h->dev.bil_tab) cudaFree(h->dev.bil_tab);
     for (auto& f : h->ev_ring) {
         cudaEventDestroy(f.t0);
         cudaEventDestroy(f.c0);
@@ -951,6 +981,75 @@ int32_t vr_last_timing_frames(const vr_handle* h) { return (h && h->timing_valid
 
 // Stand-alone temporal blend on DEVICE frames, enqueued on the handle's stream: finishes a frame-range shard's head frame
 // when the left neighbour's last un-blended frame has arrived peer-to-peer (no host staging).
+// ---- boundary frame between two handles of ONE process (pipeline.py: one host thread + handle per GPU) ----
+// vr_boundary_send: src's temporal state (its last un-blended upscaled frame) -> a device buffer on dst's device by ONE
+// cudaMemcpyPeerAsync (NVLink when the devices are peers; a plain device-to-device copy on one device), synchronised before
+// returning. Called by src's thread; only dst's boundary free list is touched (under its mutex), never dst's stream.
+int vr_boundary_send(vr_handle* src, vr_handle* dst, int32_t sH, int32_t sW, void** d_frame) {
+    if (!src || !dst || !d_frame || sH <= 0 || sW <= 0) return VR_E_INVALID;
+    if (!src->has_prev || src->prev_h != sH || src->prev_w != sW) return fail(src, VR_E_STATE, "vr_boundary_send: no previous frame of that size");
+    const size_t bytes = static_cast<size_t>(sH) * sW * 3;
+    DevBuf b;
+    {
+        std::lock_guard<std::mutex> lk(dst->bmu);
+        for (size_t i = 0; i < dst->bfree.size(); ++i)
+            if (dst->bfree[i].bytes >= bytes) {
+                b = dst->bfree[i];
+                dst->bfree.erase(dst->bfree.begin() + i);
+                break;
+            }
+    }
+    if (!b.p) {
+        VR_CUDA_CHECK(cudaSetDevice(dst->dev.ordinal), src->dev.err);
+        VR_CUDA_CHECK(cudaMalloc(&b.p, bytes), src->dev.err);
+        b.bytes = bytes;
+    }
+    VR_CUDA_CHECK(cudaSetDevice(src->dev.ordinal), src->dev.err);
+    if (src->dev.ordinal != dst->dev.ordinal) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, src->dev.ordinal, dst->dev.ordinal);
+        if (can) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(dst->dev.ordinal, 0);
+            if (pe != cudaSuccess) cudaGetLastError();  // already enabled
+        }
+        VR_CUDA_CHECK(cudaMemcpyPeerAsync(b.p, dst->dev.ordinal, src->prev_up.p, src->dev.ordinal, bytes, src->dev.stream), src->dev.err);
+    } else {
+        VR_CUDA_CHECK(cudaMemcpyAsync(b.p, src->prev_up.p, bytes, cudaMemcpyDeviceToDevice, src->dev.stream), src->dev.err);
+    }
+    VR_CUDA_CHECK(cudaStreamSynchronize(src->dev.stream), src->dev.err);
+    *d_frame = b.p;
+    return VR_OK;
+}
+
+// vr_boundary_finish: blends a chunk's head frame (host, un-blended) with the boundary frame received by vr_boundary_send and
+// writes the result to `out` (host); the boundary buffer goes back to the free list. head == NULL only recycles the buffer.
+int vr_boundary_finish(vr_handle* h, void* d_prev, const uint8_t* head, int64_t head_stride, uint8_t* out, int64_t out_stride,
+                       int32_t sH, int32_t sW, float alpha, float tau) {
+    if (!h || !d_prev) return VR_E_INVALID;
+    const size_t row = static_cast<size_t>(sW) * 3, bytes = row * sH;
+    int rc = VR_OK;
+    if (head) {
+        if (!out || sH <= 0 || sW <= 0) return fail(h, VR_E_INVALID, "vr_boundary_finish: bad arguments");
+        rc = [&]() -> int {
+            VR_CUDA_CHECK(cudaSetDevice(h->dev.ordinal), h->dev.err);
+            VR_TRY(ensure(h, h->hr[0], bytes));
+            VR_TRY(ensure(h, h->hr[1], bytes));
+            VR_CUDA_CHECK(cudaMemcpy2DAsync(h->hr[0].p, row, head, head_stride, row, sH, cudaMemcpyHostToDevice, h->dev.stream), h->dev.err);
+            VR_TRY(launch_temporal(h->dev, static_cast<const uint8_t*>(h->hr[0].p), row, static_cast<const uint8_t*>(d_prev), row, sH, sW,
+                                   static_cast<uint8_t*>(h->hr[1].p), row, alpha > 0 ? alpha : 0.2f, tau > 0 ? tau : 12.f));
+            VR_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, h->hr[1].p, row, row, sH, cudaMemcpyDeviceToHost, h->dev.stream), h->dev.err);
+            VR_CUDA_CHECK(cudaStreamSynchronize(h->dev.stream), h->dev.err);
+            return VR_OK;
+        }();
+    }
+    DevBuf b;
+    b.p = d_prev;
+    b.bytes = bytes;
+    std::lock_guard<std::mutex> lk(h->bmu);
+    h->bfree.push_back(b);
+    return rc;
+}
+
 int vr_temporal_device(vr_handle* h, const uint8_t* d_cur, const uint8_t* d_prev, int32_t sH, int32_t sW, uint8_t* d_out,
                        float alpha, float tau) {
     if (!h) return VR_E_INVALID;
@@ -986,6 +1085,7 @@ struct TmpDev {
         ok = true;
     }
     ~TmpDev() {
+        if (dev.bil_tab) cudaFree(dev.bil_tab);
         if (dev.stream) cudaStreamDestroy(dev.stream);
     }
 };

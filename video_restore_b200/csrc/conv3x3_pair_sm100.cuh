@@ -278,8 +278,14 @@ __device__ __forceinline__ bool epi_row_pair_direct(const ConvArgs& a, uint32_t 
                 epi_act32(v, amode, a.slope, s_neg + g * 32);
                 if (st) {
                     __half* o = a.out + chan_off(p, a.out_cstride, a.out_pstride, a.out_coff + g * 32);
-                    ptx::stg256(o, pack8(v), pack8(v + 8));
-                    ptx::stg256(o + 16, pack8(v + 16), pack8(v + 24));
+                    const uint4 h0 = pack8(v), h1 = pack8(v + 8), h2 = pack8(v + 16), h3 = pack8(v + 24);
+                    ptx::stg256(o, h0, h1);
+                    ptx::stg256(o + 16, h2, h3);
+                    if (a.out2) {
+                        __half* o2 = a.out2 + chan_off(p, a.out2_cstride, a.out_pstride, a.out_coff + g * 32);
+                        ptx::stg256(o2, h0, h1);
+                        ptx::stg256(o2 + 16, h2, h3);
+                    }
                 }
             }
             return true;
@@ -370,6 +376,11 @@ __device__ __forceinline__ bool epi_row_pair_direct(const ConvArgs& a, uint32_t 
             } else {
                 ptx::stg256(o, h0, h1);
                 ptx::stg256(o + 16, h2, h3);
+            }
+            if (kNoRes && a.out2) {  // second destination (conv_first): only layers without residual operands have one
+                __half* o2 = a.out2 + chan_off(p, a.out2_cstride, a.out_pstride, a.out_coff + g * 32);
+                ptx::stg256(o2, h0, h1);
+                ptx::stg256(o2 + 16, h2, h3);
             }
         }
     }

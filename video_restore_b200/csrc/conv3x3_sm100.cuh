@@ -53,6 +53,10 @@ struct ConvArgs {
     float slope;
     __half* out;
     int out_cstride, out_coff, cout;
+    // optional second destination of the same values (K3 direct epilogue only; same channel offset and plane distance as `out`):
+    // conv_first feeds both the trunk skip (`feat`) and the first dense block's x slot from one launch
+    __half* out2;
+    int out2_cstride;
     // Chunk-planar tensors: a tensor with cstride == 32 stores channels [32k, 32k+32) as plane k, [H][W][32] fp16, planes
     // `pstride` elements apart (every TMA box row and every output row is then contiguous; the interleaved [H][W][C] form
     // costs the 32-channel layers 16..52 %). Any other cstride is the interleaved form (pstride unused).

@@ -313,6 +313,7 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     int nslots = (T::kBudget + T::kStgBytes - stg_bytes - w_bytes) / T::kASlot;
     if (nslots < T::kMinSlots) return 1;
     if (nslots > kPairMaxSlots) nslots = kPairMaxSlots;
+    if (a.out2 && (!a.epi_direct || a.out2_cstride % 32 != 0 || a.res1 || a.res2)) return 1;
     // layers without residual operands get the instantiation that has no residual registers (N = 64: early ring release)
     const bool nores = a.epi_direct && !a.res1 && !a.res2;
     auto kern = nores ? conv3x3_pair_kernel<N, true, true>
@@ -363,6 +364,10 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     dev.launches++;
     dev.conv_launches++;
     return 0;
+}
+
+bool conv_supports_out2(const Device& dev, int cout) {
+    return dev.epi_direct && ((cout == 32 && (dev.rolling & 8)) || (cout == 64 && (dev.rolling & 16)));
 }
 
 void read_conv_env(Device& dev) {
@@ -428,6 +433,8 @@ int run_conv(Device& dev, const ConvCall& c) {
     a.out = c.out;
     a.out_cstride = c.out_cstride;
     a.out_coff = c.out_coff;
+    a.out2 = c.out2;
+    a.out2_cstride = c.out2_cstride;
     a.cout = w.cout;
     a.res1 = c.res1;
     a.res1_cstride = c.res1_cstride;
@@ -493,12 +500,20 @@ int run_conv(Device& dev, const ConvCall& c) {
         if (w.cout == 32 && (mask & 8)) rc = launch_pair<32>(dev, tm1, a, w);
         if (w.cout == 64 && (mask & 16)) rc = launch_pair<64>(dev, tm1, a, w);
         if (rc <= 0) return rc;
+        if (c.out2) {
+            set_error(dev.err, "run_conv: a second destination needs the K3 direct epilogue (conv_supports_out2)");
+            return -1;
+        }
         if (w.cout == 32 && (mask & 1)) rc = launch_roll<32>(dev, tm1, a, w);
         if (w.cout == 64 && (mask & 2)) rc = launch_roll<64>(dev, tm1, a, w);                    // whole layer resident
         if (w.cout == 64 && rc == 1 && (mask & 4) && w.wsplit &&
             w.nchunks * RollTraits<64>::kBStage + RollTraits<64>::kMinSlots * RollTraits<64>::kASlot > RollTraits<64>::kBudget)
             rc = launch_roll<32>(dev, tm1, a, w);                                               // two resident halves
         if (rc <= 0) return rc;
+    }
+    if (c.out2) {
+        set_error(dev.err, "run_conv: a second destination needs the K3 direct epilogue (conv_supports_out2)");
+        return -1;
     }
     if (c.flags & (FLAG_FORCE_ROLL | FLAG_FORCE_PAIR)) {
         set_error(dev.err, "run_conv: the rolling-row kernels do not take this layer");

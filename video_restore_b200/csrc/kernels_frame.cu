@@ -283,18 +283,27 @@ struct BilateralParams {
     int8_t dy[49], dx[49];
     float space_w[49];
 };
-__constant__ BilateralParams c_bil;
-__constant__ float c_color_w[768];
+// Tables live in GLOBAL memory owned by the Device (one per handle), not in __constant__ symbols: constants are per-device
+// globals shared by every handle and stream, so two restorers on one GPU with different sigma / d would overwrite each
+// other's tables under a running kernel, and refreshing them needed a host sync inside the per-frame enqueue.
+struct BilateralTables {
+    BilateralParams bp;
+    float color_w[768];
+};
 
 constexpr int kBilBW = 32, kBilBH = 8, kBilMaxR = 3;
 __global__ void __launch_bounds__(kBilBW* kBilBH)
 bilateral_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int W, uint8_t* __restrict__ dst,
-                 int64_t dstride) {
+                 int64_t dstride, const BilateralTables* __restrict__ tab) {
     __shared__ uint8_t tile[kBilBH + 2 * kBilMaxR][(kBilBW + 2 * kBilMaxR) * 3 + 2];
     __shared__ float s_color[768];
-    const int R = c_bil.radius;
+    __shared__ BilateralParams c_bil;
     const int tid = threadIdx.y * kBilBW + threadIdx.x;
-    for (int i = tid; i < 768; i += kBilBW * kBilBH) s_color[i] = c_color_w[i];
+    for (int i = tid; i < 768; i += kBilBW * kBilBH) s_color[i] = __ldg(tab->color_w + i);
+    for (int i = tid; i < static_cast<int>(sizeof(BilateralParams) / 4); i += kBilBW * kBilBH)
+        reinterpret_cast<uint32_t*>(&c_bil)[i] = __ldg(reinterpret_cast<const uint32_t*>(&tab->bp) + i);
+    __syncthreads();
+    const int R = c_bil.radius;
     const int bx0 = blockIdx.x * kBilBW - R, by0 = blockIdx.y * kBilBH - R;
     const int tw = kBilBW + 2 * R, th = kBilBH + 2 * R;
     for (int i = tid; i < tw * th; i += kBilBW * kBilBH) {
@@ -339,7 +348,10 @@ int launch_bilateral(Device& dev, const uint8_t* src, int64_t sstride, int H, in
         set_error(dev.err, "bilateral: radius > 3 (d > 7) not supported");
         return -1;
     }
-    BilateralParams bp;
+    if (!dev.bil_tab || dev.bil_d != d || dev.bil_sc != sigma_color || dev.bil_ss != sigma_space) {
+    dev.bil_host.resize(sizeof(BilateralTables));
+    BilateralTables& bt = *reinterpret_cast<BilateralTables*>(dev.bil_host.data());
+    BilateralParams& bp = bt.bp;
     std::memset(&bp, 0, sizeof(bp));
     bp.radius = radius;
     int maxk = 0;
@@ -353,13 +365,20 @@ int launch_bilateral(Device& dev, const uint8_t* src, int64_t sstride, int H, in
             ++maxk;
         }
     bp.maxk = maxk;
-    float cw[768];
-    for (int i = 0; i < 768; ++i) cw[i] = static_cast<float>(std::exp(static_cast<double>(i) * i * gcc));
-    VR_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_bil, &bp, sizeof(bp), 0, cudaMemcpyHostToDevice, dev.stream), dev.err);
-    VR_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_color_w, cw, sizeof(cw), 0, cudaMemcpyHostToDevice, dev.stream), dev.err);
-    VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);  // stack tables
+    for (int i = 0; i < 768; ++i) bt.color_w[i] = static_cast<float>(std::exp(static_cast<double>(i) * i * gcc));
+    // uploaded only when (d, sigma_color, sigma_space) change; stream-ordered behind the kernels still reading the old tables.
+    // The staging copy lives in the Device, but a second change may follow at once: wait for the previous upload first.
+    if (!dev.bil_tab) VR_CUDA_CHECK(cudaMalloc(&dev.bil_tab, sizeof(BilateralTables)), dev.err);
+    VR_CUDA_CHECK(cudaMemcpyAsync(dev.bil_tab, dev.bil_host.data(), sizeof(BilateralTables), cudaMemcpyHostToDevice, dev.stream),
+                  dev.err);
+    VR_CUDA_CHECK(cudaStreamSynchronize(dev.stream), dev.err);  // once per parameter change, not per frame
+    dev.bil_d = d;
+    dev.bil_sc = sigma_color;
+    dev.bil_ss = sigma_space;
+    }
     dim3 block(kBilBW, kBilBH), grid((W + kBilBW - 1) / kBilBW, (H + kBilBH - 1) / kBilBH);
-    bilateral_kernel<<<grid, block, 0, dev.stream>>>(src, sstride, H, W, dst, dstride);
+    bilateral_kernel<<<grid, block, 0, dev.stream>>>(src, sstride, H, W, dst, dstride,
+                                                     static_cast<const BilateralTables*>(dev.bil_tab));
     VR_LAUNCH_CHECK(dev);
     return 0;
 }

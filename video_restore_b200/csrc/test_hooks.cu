@@ -45,6 +45,7 @@ struct ScopedDev {
         ok = true;
     }
     ~ScopedDev() {
+        if (dev.bil_tab) cudaFree(dev.bil_tab);
         if (dev.stream) cudaStreamDestroy(dev.stream);
     }
 };

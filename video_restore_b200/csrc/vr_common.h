@@ -50,6 +50,8 @@ struct ConvCall {
     float slope = 0.2f;
     __half* out = nullptr;
     int out_cstride = 0, out_coff = 0;
+    __half* out2 = nullptr;  // optional second destination (K3 direct epilogue only), same channel offset / plane distance
+    int out2_cstride = 0;
     long long out_pstride = 0, res1_pstride = 0, res2_pstride = 0;  // plane distances (cstride == 32 tensors)
     const __half* res1 = nullptr;
     int res1_cstride = 0, res1_coff = 0;
@@ -83,6 +85,11 @@ struct Device {
     std::string* err = nullptr;
     int64_t launches = 0;
     int64_t conv_launches = 0;  // of which convolution kernels (K1 / K2 / K3 / K4)
+    // bilateral tables of this handle (device global memory), rebuilt only when the parameters change
+    void* bil_tab = nullptr;
+    int bil_d = -1;
+    float bil_sc = -1.f, bil_ss = -1.f;
+    std::vector<char> bil_host;
     // dependency counters of multi-layer launches: two regions used alternately (each launch zeroes the other one)
     int* dep_buf = nullptr;
     int dep_parity = 0;
@@ -119,6 +126,7 @@ int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const
                       ConvWeights* out, int kc = 0);  // kc = 0: default (env VR_KC or 32)
 void free_conv_weights(ConvWeights* w);
 int run_conv(Device& dev, const ConvCall& c);
+bool conv_supports_out2(const Device& dev, int cout);  // the configured kernel for a `cout`-channel NHWC layer takes ConvCall::out2
 // reads every conv-related environment switch into `dev` (called when a handle / test device is created, so that one
 // process can run several configurations)
 void read_conv_env(Device& dev);

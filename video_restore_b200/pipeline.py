@@ -85,36 +85,149 @@ class ArraySource:
 
 
 class VideoFileSource:
-    """OpenCV-decoded video file (stands in for the reference's ffmpeg rawvideo pipe, :220-249). Every worker thread
-    gets its own `cv2.VideoCapture` (`reader()`) and decodes its chunks sequentially. Getting to the start of a chunk:
-    seek="set" uses CAP_PROP_POS_FRAMES (fast; exact for intra-coded and most indexed containers, but OpenCV's backends
-    may land on a neighbouring frame in some inter-coded streams); seek="grab" never seeks -- it skips forward with
-    grab() from wherever the reader is (always exact, costs the decode of the skipped frames)."""
+    """OpenCV-decoded video file (stands in for the reference's ffmpeg rawvideo pipe, :220-249).
 
-    def __init__(self, path: str, seek: str = "set"):
+    Frame count: container metadata is a HINT (0, negative, too small or too large all occur; the reference falls back to
+    `ffprobe -count_frames`, video_upscaler.py:195-203, and to "decode until EOF", :450, :540). Unless `trust_count=True` the
+    frames are counted exactly up front with one grab() pass (no colour conversion; far cheaper than restoring them).
+
+    Getting to the start of a chunk, `seek`:
+      "sequential" (default) -- ONE decoder thread reads the file front to back, like the reference's single decode thread
+          (:430-451), and hands every frame to whichever worker asks for its index (bounded look-ahead): never seeks, exact on
+          any stream, decodes every frame once. Needs interleaved chunks (the CLI's 16-frame chunks); with one long range per
+          worker the readers fall back to "grab".
+      "grab" -- one decoder per worker that never seeks: skips forward with grab() (exact, decodes skipped frames).
+      "set"  -- one decoder per worker, CAP_PROP_POS_FRAMES seeks (fast; OpenCV's backends may land on a neighbouring frame in
+          inter-coded streams, so duplicated / dropped frames at chunk boundaries are possible: opt-in only)."""
+
+    def __init__(self, path: str, seek: str = "sequential", trust_count: bool = False, lookahead: int = 256):
         import cv2
 
-        if seek not in ("set", "grab"):
-            raise ValueError("seek must be 'set' or 'grab'")
-        self.path, self.seek = str(path), seek
+        if seek not in ("sequential", "set", "grab"):
+            raise ValueError("seek must be 'sequential', 'grab' or 'set'")
+        self.path, self.seek, self.lookahead = str(path), seek, int(lookahead)
         cap = cv2.VideoCapture(self.path)
         if not cap.isOpened():
             raise OSError(f"cannot open {self.path}")
-        self.n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        hint = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
         self.fps = float(cap.get(cv2.CAP_PROP_FPS) or 30.0)
         self.width = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH))
         self.height = int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+        if trust_count and hint > 0:
+            self.n = hint
+        else:
+            n = 0
+            while cap.grab():
+                n += 1
+            self.n = n
+        self.count_hint = hint
         cap.release()
+        self._dispatch = None
+        self._lock = threading.Lock()
 
     def __len__(self) -> int:
         return self.n
 
-    def reader(self) -> "_VideoReader":
-        return _VideoReader(self.path, self.seek)
+    def reader(self, long_ranges: bool = False):
+        """A reader for one worker thread. `long_ranges`: the caller walks one long contiguous range per worker, which a
+        shared sequential decoder would serialise."""
+        if self.seek == "sequential" and not long_ranges:
+            with self._lock:
+                if self._dispatch is None:
+                    self._dispatch = _SequentialDecoder(self.path, self.lookahead)
+            return _SharedReader(self._dispatch)
+        return _VideoReader(self.path, "grab" if self.seek == "sequential" else self.seek)
+
+    def close(self) -> None:
+        if self._dispatch is not None:
+            self._dispatch.stop()
+            self._dispatch = None
+
+
+class _SequentialDecoder:
+    """One thread decoding the file front to back into a bounded index -> frame map; consumers take frames by index (each
+    frame once; frame 0 stays available for the workers' warm-up reads)."""
+
+    def __init__(self, path: str, lookahead: int):
+        import cv2
+
+        self._cap = cv2.VideoCapture(path)
+        self._cv = threading.Condition()
+        self._frames: dict = {}
+        self._first = None
+        self._next = 0            # next index to decode
+        self._eof: Optional[int] = None
+        self._stop = False
+        self._lookahead = max(lookahead, 4)
+        self._waiting: set = set()  # indices consumers are blocked on
+        self._thread = threading.Thread(target=self._run, name="vr-decode", daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        while True:
+            with self._cv:
+                # bounded look-ahead, except that a frame somebody is waiting for is always decoded (no deadlock on a full map)
+                while (not self._stop and len(self._frames) >= self._lookahead
+                       and not any(w >= self._next for w in self._waiting)):
+                    self._cv.wait(0.2)
+                if self._stop:
+                    break
+            ok, frame = self._cap.read()
+            with self._cv:
+                if not ok:
+                    self._eof = self._next
+                    self._cv.notify_all()
+                    break
+                if self._next == 0:
+                    self._first = frame
+                self._frames[self._next] = frame
+                self._next += 1
+                self._cv.notify_all()
+        self._cap.release()
+
+    def take(self, i: int):
+        with self._cv:
+            if i == 0 and self._first is not None:
+                self._frames.pop(0, None)
+                return self._first
+            self._waiting.add(i)
+            try:
+                while i not in self._frames:
+                    if i == 0 and self._first is not None:
+                        return self._first
+                    if self._eof is not None and i >= self._eof:
+                        return None
+                    if i < self._next:
+                        raise RuntimeError(f"frame {i} was already consumed (the sequential decoder hands every frame out once)")
+                    if self._stop:
+                        return None
+                    self._cv.notify_all()
+                    self._cv.wait(0.2)
+                return self._frames.pop(i)
+            finally:
+                self._waiting.discard(i)
+                self._cv.notify_all()
+
+    def stop(self) -> None:
+        with self._cv:
+            self._stop = True
+            self._cv.notify_all()
+
+
+class _SharedReader:
+    def __init__(self, dec: _SequentialDecoder):
+        self._dec = dec
+
+    def read_range(self, start: int, end: int):
+        for i in range(start, end):
+            f = self._dec.take(i)
+            if f is None:
+                return
+            yield f
 
 
 class _VideoReader:
-    def __init__(self, path: str, seek: str = "set"):
+    def __init__(self, path: str, seek: str = "grab"):
         import cv2
 
         self._cv2 = cv2
@@ -378,6 +491,13 @@ class OrderedReassembler:
 # ---------------------------------------------------------------------------------------------------------------
 # boundary frames
 # ---------------------------------------------------------------------------------------------------------------
+class _DeviceBoundary:
+    """A boundary frame that already sits in device memory of the consuming restorer's GPU (FrameRestorer.boundary_send)."""
+
+    def __init__(self, ptr: int):
+        self.ptr = ptr
+
+
 class _Boundaries:
     """u_last of chunk c, published by its worker for the worker of chunk c + 1 (one frame per chunk boundary)."""
 
@@ -455,6 +575,7 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
     reasm = OrderedReassembler(sink, total, capacity)
     bounds = _Boundaries()
     make_blend = temporal_blend or _default_temporal_blend
+    peer = temporal_blend is None  # a caller-supplied blend (tests, stubs) keeps the host path
     stats = PipelineStats(chunks=len(plan))
     errors: List[BaseException] = []
     lock = threading.Lock()
@@ -464,8 +585,12 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
         restorer = None
         try:
             restorer = make_restorer(gpu)
+            restorers[slot] = restorer
             blend = make_blend(gpu)
-            reader = source.reader()
+            try:
+                reader = source.reader(long_ranges=chunk is None and G > 1)
+            except TypeError:  # sources without the keyword (synthetic / array / user-supplied)
+                reader = source.reader()
             zero_copy = bool(getattr(restorer, "zero_copy_stream", False))
             if zero_copy:
                 with lock:
@@ -507,15 +632,33 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
                 if use_temporal and ci + 1 < len(plan) and out_shape is None:
                     bounds.publish(ci, None)  # nothing decoded: the next chunk (past the end) must not wait
                 if use_temporal and ci + 1 < len(plan) and out_shape is not None:
-                    if zero_copy:
+                    nxt = restorers[plan[ci + 1][2]]
+                    if peer and getattr(nxt, "peer_boundary", False):
+                        # ONE cudaMemcpyPeerAsync: this GPU's last un-blended frame -> a device buffer on the next chunk's GPU
+                        b = _DeviceBoundary(restorer.boundary_send(nxt, out_shape[0], out_shape[1]))
+                    elif zero_copy:
                         b = pool[0].get(out_shape)
                         restorer.temporal_get_prev(out_shape[0], out_shape[1], out=b)
                     else:
                         b = restorer.temporal_get_prev(out_shape[0], out_shape[1])
                     bounds.publish(ci, b)
-                if defer_head and head is not None:
+                if defer_head:
                     prev = bounds.take(ci - 1)
-                    if prev is None:
+                    if isinstance(prev, _DeviceBoundary):
+                        if head is None:
+                            restorer.boundary_finish(prev.ptr, None, None)   # nothing decoded for this chunk: recycle only
+                        else:
+                            with lock:
+                                stats.boundary_frames += 1
+                            dst = pool[0].get(head.shape) if zero_copy else np.empty_like(head)
+                            restorer.boundary_finish(prev.ptr, head, dst, opts.temporal_alpha, opts.temporal_tau)
+                            reasm.put(s, dst, give_back)
+                            if zero_copy:
+                                give_back(head)
+                    elif head is None:
+                        if prev is not None and zero_copy:
+                            give_back(prev)
+                    elif prev is None:
                         reasm.put(s, head, give_back)
                     else:
                         with lock:
@@ -539,6 +682,7 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
     t0 = time.perf_counter()
     t_start = [t0]
     pool: List[Optional[BufferPool]] = [None]
+    restorers: List[object] = [None] * G   # filled by the workers before the start barrier
     ready = threading.Barrier(G)
     threads = [threading.Thread(target=worker, args=(i,), name=f"vr-gpu{gpu_ids[i]}", daemon=True) for i in range(G)]
     for t in threads:
@@ -563,4 +707,6 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
     if pool[0] is not None:
         reasm._free.clear()
         pool[0].close()
+    if hasattr(source, "close"):
+        source.close()
     return stats

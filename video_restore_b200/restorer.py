@@ -94,6 +94,9 @@ class FrameRestorer:
         s = self.scale
         if out is None:
             out = np.empty((H * s, W * s, 3), np.uint8)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != (H * s, W * s, 3)
+              or out.strides[1:] != (3, 1) or out.strides[0] < W * s * 3 or not out.flags.writeable):
+            raise ValueError(f"out must be a writable uint8 array of shape {(H * s, W * s, 3)} with dense pixels")
         o = (opts or FrameOpts()).to_c()
         rc = self._lib.vr_restore(self._h, frame.ctypes.data_as(C.c_void_p), H, W, frame.strides[0],
                                   out.ctypes.data_as(C.c_void_p), out.strides[0], C.byref(o))
@@ -182,6 +185,8 @@ class FrameRestorer:
             _lib.check(self._lib.vr_temporal_get_prev(self._h, C.c_void_p(int(device_ptr)), sH, sW, sW * 3, 1), self._h)
             return None
         a = out if out is not None else np.empty((sH, sW, 3), np.uint8)
+        if a.dtype != np.uint8 or a.shape != (sH, sW, 3) or a.strides[1:] != (3, 1) or not a.flags.writeable:
+            raise ValueError(f"out must be a writable uint8 array of shape {(sH, sW, 3)} with dense pixels")
         _lib.check(self._lib.vr_temporal_get_prev(self._h, a.ctypes.data_as(C.c_void_p), sH, sW, a.strides[0], 0),
                    self._h)
         return a
@@ -191,6 +196,29 @@ class FrameRestorer:
         """Temporal blend of two device frames on this restorer's stream (asynchronous; `sync()` to wait)."""
         _lib.check(self._lib.vr_temporal_device(self._h, C.c_void_p(int(d_cur)), C.c_void_p(int(d_prev)), sH, sW,
                                                 C.c_void_p(int(d_out)), alpha, tau), self._h)
+
+    # -- boundary frame between two restorers of one process (pipeline.py) ---------------------------
+    peer_boundary = True
+
+    def boundary_send(self, dst: "FrameRestorer", sH: int, sW: int) -> int:
+        """This restorer's last un-blended frame -> a device buffer on `dst`'s GPU (one cudaMemcpyPeerAsync); returns the
+        device pointer, to be handed to dst.boundary_finish by dst's thread."""
+        p = C.c_void_p()
+        _lib.check(self._lib.vr_boundary_send(self._h, dst._h, sH, sW, C.byref(p)), self._h)
+        return int(p.value)
+
+    def boundary_finish(self, d_prev: int, head: np.ndarray | None, out: np.ndarray | None, alpha: float = 0.2,
+                        tau: float = 12.0) -> None:
+        """Blend the host head frame with the received boundary frame into `out` (host); recycles the device buffer."""
+        if head is None:
+            _lib.check(self._lib.vr_boundary_finish(self._h, C.c_void_p(d_prev), None, 0, None, 0, 0, 0, alpha, tau), self._h)
+            return
+        if head.dtype != np.uint8 or out.dtype != np.uint8 or head.shape != out.shape or head.strides[1:] != (3, 1) \
+                or out.strides[1:] != (3, 1):
+            raise ValueError("boundary_finish: head / out must be uint8 HxWx3 with dense rows")
+        _lib.check(self._lib.vr_boundary_finish(self._h, C.c_void_p(d_prev), head.ctypes.data_as(C.c_void_p), head.strides[0],
+                                                out.ctypes.data_as(C.c_void_p), out.strides[0], head.shape[0], head.shape[1],
+                                                alpha, tau), self._h)
 
     # -- introspection ---------------------------------------------------------------------------
     @property
@@ -266,19 +294,29 @@ class RealESRGANer:
         self.tile_pad = tile_pad
         self.pre_pad = pre_pad
         self.half = half
-        self._r = FrameRestorer(model=spec, state_dict=state_dict, tile=tile, tile_pad=tile_pad, pre_pad=pre_pad,
+        if pre_pad < 0:
+            raise ValueError("pre_pad must be >= 0")
+        # pre_pad (upstream default 10; the reference passes 0, video_upscaler.py:334) is a reflect pad of the bottom / right
+        # edge before everything else and a crop afterwards: done here on the host frame, the C ABI always sees pre_pad = 0
+        self._r = FrameRestorer(model=spec, state_dict=state_dict, tile=tile, tile_pad=tile_pad, pre_pad=0,
                                 blend=blend, gpu_id=gpu_id)
 
     def enhance(self, img, outscale=None, alpha_upsampler="realesrgan"):
         """uint8 HxWx3 BGR -> (uint8 BGR, 'RGB') like upstream. The reference always passes outscale == scale
         (video_upscaler.py:501,718); any other outscale is upstream's final step, a Lanczos resize of the network-scale
         result on the host with the very same OpenCV call."""
+        h0, w0 = img.shape[:2]
+        if self.pre_pad:
+            if self.pre_pad >= min(h0, w0):
+                raise ValueError("pre_pad must be smaller than the frame (reflect padding)")
+            img = np.pad(img, ((0, self.pre_pad), (0, self.pre_pad), (0, 0)), mode="reflect")
         out = self._r.process_frame(img)
+        if self.pre_pad:
+            out = np.ascontiguousarray(out[:h0 * self.scale, :w0 * self.scale])
         if outscale is not None and float(outscale) != float(self.scale):
             import cv2
 
-            h, w = img.shape[:2]
-            out = cv2.resize(out, (int(w * outscale), int(h * outscale)), interpolation=cv2.INTER_LANCZOS4)
+            out = cv2.resize(out, (int(w0 * outscale), int(h0 * outscale)), interpolation=cv2.INTER_LANCZOS4)
         return out, "RGB"
 
 

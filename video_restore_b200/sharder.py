@@ -201,12 +201,18 @@ class FrameRangeSharder:
         put_frame(self.start, self._finish_head(restorer, head, opts, temporal_blend))
         return n
 
-    def run_stream(self, restorer, get_frame, put_frame, opts, temporal_blend: Callable | None = None) -> int:
-        """As run(defer_head=True) over the restorer's pipelined host path (process_stream: H2D / compute / D2H of
-        neighbouring frames overlapped). Frames handed to put_frame are views of pinned ring buffers, valid until the
-        next-but-two call."""
+    def run_stream(self, restorer, get_frame, put_frame, opts, temporal_blend: Callable | None = None,
+                   defer_head: bool = True) -> int:
+        """As run() over the restorer's pipelined host path (process_stream: H2D / compute / D2H of neighbouring frames
+        overlapped). Frames handed to put_frame are views of pinned ring buffers, valid until the next-but-two call.
+        defer_head=False delivers strictly in order (a sequential encoder) at the price of one extra frame per shard."""
         n = self.end - self.start
-        deferred = bool(opts.temporal) and self.world > 1
+        deferred = bool(opts.temporal) and self.world > 1 and defer_head
+        if bool(opts.temporal) and self.world > 1 and not defer_head:
+            self.exchange_boundary(restorer, get_frame, opts)
+            for k, out in enumerate(restorer.process_stream((get_frame(i) for i in range(self.start, self.end)), opts)):
+                put_frame(self.start + k, out)
+            return n
         if deferred:
             if n == 0:
                 raise ValueError("empty shard: need total_frames >= world size when the temporal stage is on")
