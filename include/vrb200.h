@@ -168,6 +168,12 @@ typedef struct vr_conv_test {
 int vr_conv3x3_test(vr_conv_test* t);
 const char* vr_global_error(void);
 
+/* K4 test / bench hook: two consecutive 32-channel dense-block layers (cin -> 32, cin + 32 -> 32, bias + LeakyReLU) in ONE launch
+ * over a chunk-planar buffer, x [H][W][cin] (cin % 32 == 0), ya / yb [H][W][32]; optional tile-atlas gap columns / rows. */
+int vr_conv_pair2_test(int32_t device, int32_t H, int32_t W, int32_t cin, const float* x, const float* wa, const float* ba,
+                       const float* wb, const float* bb, float slope, float* ya, float* yb, int32_t iters, float* ms,
+                       const int32_t* gaps_x, int32_t ngx, const int32_t* gaps_y, int32_t ngy);
+
 /* Device-resident conv benchmark on zero-copy synthetic data: returns average ms per launch. */
 int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t rows,
                      int32_t flags, int32_t iters, float* ms_out);

@@ -432,16 +432,23 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
     # accumulator's initial value, taps are summed row by row), so the 8-bit frames agree within one level
     # interleaved instead of chunk-planar activation tensors: same arithmetic in the same order
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_PLANAR": "0"})[0])
-    k3 = run({})[0]
-    assert np.array_equal(k3, run({"VR_PLANAR": "0"})[0])
+    # K3 everywhere (VR_K4=0: the dense block's layer pairs as separate launches; K4 itself is tests/test_gpu_k4.py)
+    k3 = run({"VR_K4": "0"})[0]
+    assert np.array_equal(k3, run({"VR_K4": "0", "VR_PLANAR": "0"})[0])
     # K3 epilogue variants: staged through shared memory instead of direct 256-bit stores, ring position handed back after the
     # stores / before them / right after the TMEM loads -- the arithmetic and its order are the same
     for env in ({"VR_EPI_DIRECT": "0"}, {"VR_EARLY64": "0"}, {"VR_EARLY64": "1"}, {"VR_EPI_DIRECT": "0", "VR_EARLY64": "0"}):
-        assert np.array_equal(k3, run(env)[0]), env
+        assert np.array_equal(k3, run({"VR_K4": "0", **env})[0]), env
+    # the default path (K4 pairs + K3): the same switches only touch its K3 layers -- still bit-identical to itself
+    k4 = run({})[0]
+    for env in ({"VR_EARLY64": "0"}, {"VR_EARLY64": "1"}, {"VR_PDL": "0"}):
+        assert np.array_equal(k4, run(env)[0]), env
+    d = np.abs(k4.astype(np.int32) - k3.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 3e-2
     # a different issuer hand-over granularity moves the points where the two issuing warps alternate; MMAs of different
     # warps into one accumulator are applied in a different order then (measured: not bit-identical), within tolerance
-    u1 = run({"VR_UNIT": "1"})[0]
-    assert np.array_equal(u1, run({"VR_UNIT": "1"})[0])
+    u1 = run({"VR_K4": "0", "VR_UNIT": "1"})[0]
+    assert np.array_equal(u1, run({"VR_K4": "0", "VR_UNIT": "1"})[0])
     d = np.abs(u1.astype(np.int32) - k3.astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 2e-2
     for mask in ("1", "7", "24", "31"):

@@ -81,6 +81,9 @@ SIGNATURES = {
                               C.c_float]),
     "vr_blend_weights": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p]),
     "vr_conv3x3_test": (C.c_int, [C.POINTER(VrConvTest)]),
+    "vr_conv_pair2_test": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_void_p,
+                                     C.c_int32, C.c_void_p, C.c_int32]),
     "vr_global_error": (C.c_char_p, []),
     "vr_conv3x3_bench": (C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_float)]),
     "vr_last_conv_cycles": (C.c_int64, []),
@@ -148,6 +151,23 @@ def conv3x3(x, weight, bias=None, act=0, slope=0.2, prelu=None, res1=None, s1=1.
                    rows=rows, flags=flags, iters=iters, ms=0.0, device=device)
     check(lib.vr_conv3x3_test(C.byref(t)))
     return y, float(t.ms)
+
+
+def conv_pair2(x, wa, ba, wb, bb, slope=0.2, iters=1, gaps_x=(), gaps_y=(), device=0):
+    """K4 hook: x [H,W,Cin] (Cin % 32 == 0); layer A Cin -> 32, layer B Cin + 32 -> 32 (input = concat(x, yA)), both with bias and
+    LeakyReLU. Returns (yA, yB, ms)."""
+    lib = load()
+    x = _f32(x); wa = _f32(wa); ba = _f32(ba); wb = _f32(wb); bb = _f32(bb)
+    H, W, cin = x.shape
+    ya = np.zeros((H, W, 32), np.float32)
+    yb = np.zeros((H, W, 32), np.float32)
+    gx = np.asarray(gaps_x, np.int32)
+    gy = np.asarray(gaps_y, np.int32)
+    ms = C.c_float(0)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    check(lib.vr_conv_pair2_test(device, H, W, cin, ptr(x), ptr(wa), ptr(ba), ptr(wb), ptr(bb), slope, ptr(ya), ptr(yb), iters,
+                                 C.byref(ms), ptr(gx) if gx.size else None, gx.size, ptr(gy) if gy.size else None, gy.size))
+    return ya, yb, float(ms.value)
 
 
 def conv3x3_bench(H, W, cin, cout, rows=0, flags=0, iters=20, device=0) -> float:

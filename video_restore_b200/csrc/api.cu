@@ -303,6 +303,32 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
                         mc.gy[i] = h->gaps.gy[i];
                     }
                     VR_TRY(run_conv(h->dev, mc));
+                } else if (conv_supports_pair2(h->dev) && band >= nh) {
+                    // K4: conv1 + conv2 and conv3 + conv4 as two launches; the second layer of each pair reads x .. x_{k-1} from
+                    // L2 and x_k from shared memory instead of HBM (26 -> 18 plane transfers per dense block)
+                    for (int k = 1; k <= 3; k += 2) {
+                        const ConvWeights* wa = layer(h, pre + std::to_string(k));
+                        const ConvWeights* wb = layer(h, pre + std::to_string(k + 1));
+                        if (!wa || !wb) return fail(h, VR_E_STATE, "missing layer " + pre + std::to_string(k));
+                        ConvCall pc;
+                        set_io(pc, X, X);
+                        pc.H = nh;
+                        pc.W = nw;
+                        pc.w = wa;
+                        pc.w2 = wb;
+                        pc.act = ACT_LRELU;
+                        pc.slope = 0.2f;
+                        pc.out_coff = 64 + 32 * (k - 1);
+                        pc.out_coff2 = 64 + 32 * k;
+                        pc.ngx = h->gaps.ngx;
+                        pc.ngy = h->gaps.ngy;
+                        pc.gshift = h->gap_shift;
+                        for (int i = 0; i < 7; ++i) {
+                            pc.gx[i] = h->gaps.gx[i];
+                            pc.gy[i] = h->gaps.gy[i];
+                        }
+                        VR_TRY(run_conv(h->dev, pc));
+                    }
                 } else
                 for (int k = 1; k <= 4; ++k) {
                     const Rows rr{std::max(b0 - (5 - k), 0), std::min(b1 + (5 - k), nh)};

@@ -1,0 +1,407 @@
+// K4: TWO consecutive 32-channel layers of a dense block (conv_k and conv_k+1) in ONE launch of the CTA-pair rolling-row
+// kernel K3 (conv3x3_pair_sm100.cuh) -- the dense block's HBM bytes, not its MMAs, set the sustained frame rate.
+//
+// Layer A = conv_k reads planes x, x1..x_{k-1} and produces x_k; layer B = conv_{k+1} reads the SAME planes plus x_k. In
+// separate launches B re-reads everything from HBM (each plane is 59 MB at 720p, the L2 holds two). Here a CTA pair walks its
+// (strip, band) once for both layers, B two row pairs behind A:
+//   * B's activation boxes of x .. x_{k-1} are the rows A fetched a few microseconds earlier: L2 hits, no DRAM traffic;
+//   * B's x_k operand never leaves the SM: A's epilogue writes each finished x_k row (fp16, after bias + LeakyReLU + gap
+//     zeroing) straight into a shared-memory HAND-OFF slot in the swizzled K-major layout the MMA descriptors expect (what a
+//     TMA box of that row would have produced), fences it for the async proxy and arrives on the leader's barrier; the same row
+//     also goes to the x_k plane in global memory for the later layers of the block.
+// No CTA ever waits for another CTA pair: everything B needs beyond its own strip / band is RECOMPUTED locally --
+//   * columns: strips are 126 output pixels wide (stride 126, the MMA tile stays 128): A's 128 columns are B's 126 columns
+//     plus their one-pixel halo; B's outermost two columns are discarded. Cost: 128 / 126 = 1.6 % more MMA work;
+//   * rows: A computes its band plus ONE row above and below (nrow + 2 rows; B's vertical halo). Cost: 2 / band of layer A.
+//   A's halo rows / columns are used through the hand-off only and never stored, so every x_k element in global memory has ONE
+//   writer (K3's summation order depends on the ring position; two writers would not be bit-identical).
+// TMEM: two rings with K3's N = 64 geometry (period 6 + 2 mirror blocks of 32 columns = 256 columns each). Shared memory:
+// both layers' weight halves resident (46 / 83 KB per CTA for conv1+2 / conv3+4), 2 hand-off slots, 6..8 TMA slots.
+// Issue order per step s: the nchA boxes of A's row pair s, then the nchA + 1 boxes of B's row pair s - 2 (hand-off box last),
+// walked by the same two alternating issuer warps as K3. DRAM traffic of a dense block: 26 -> 18 plane transfers (-31 %).
+#pragma once
+#include "conv3x3_pair_sm100.cuh"
+
+namespace vr {
+
+struct Pair2 {
+    using T = PairTraits<32>;
+    static constexpr int N = 32;
+    static constexpr uint32_t P = 6;         // logical ring period per layer
+    static constexpr int kPhys = 8;          // physical blocks per layer (two mirrors)
+    static constexpr int kRingCols = 256;    // TMEM columns per layer
+    static constexpr int kHand = 2;          // hand-off slots (row pairs of x_k in flight between A's epilogue and B's MMAs)
+    static constexpr int kLag = 2;           // B runs this many row pairs behind A
+    static constexpr int kStrip = 126;       // output pixels per strip
+    static constexpr int kThreads = T::kThreads;
+    static constexpr int kBudget = 227 * 1024 - 1024 - 4096;   // dynamic shared memory: weights + hand-off + TMA slots
+    static constexpr int kMinSlots = 4;
+};
+
+// The static box sequence of one work item: step s = A's row pair s (chunks 0..nchA-1), then B's row pair s - kLag (chunks
+// 0..nchA-1 from TMA, chunk nchA from the hand-off slot).
+struct Pair2Iter {
+    int nA2, nB2, nchA, S;
+    int s, part, c;
+    __device__ __forceinline__ void init(int nin2B, int nch_a) {
+        nB2 = nin2B >> 1;
+        nA2 = nB2 + 1;
+        nchA = nch_a;
+        S = nB2 + Pair2::kLag;
+        s = 0;
+        part = 0;
+        c = 0;
+        normalize();
+    }
+    __device__ __forceinline__ bool done() const { return s >= S; }
+    __device__ __forceinline__ void normalize() {
+        while (s < S) {
+            if (part == 0) {
+                if (s < nA2) return;
+                part = 1;
+                c = 0;
+            }
+            const int b = s - Pair2::kLag;
+            if (b >= 0 && b < nB2) return;
+            part = 0;
+            c = 0;
+            ++s;
+        }
+    }
+    __device__ __forceinline__ void next() {
+        const int n = part == 0 ? nchA : nchA + 1;
+        if (++c == n) {
+            c = 0;
+            if (part == 0) part = 1;
+            else {
+                part = 0;
+                ++s;
+            }
+            normalize();
+        }
+    }
+    __device__ __forceinline__ int pair_index() const { return part == 0 ? s : s - Pair2::kLag; }
+    __device__ __forceinline__ bool hand() const { return part == 1 && c == nchA; }
+    __device__ __forceinline__ bool last_chunk() const { return c == (part == 0 ? nchA - 1 : nchA); }
+    __device__ __forceinline__ int boxes() const { return nA2 * nchA + nB2 * (nchA + 1); }
+};
+
+// sub-items as in K3, strips of 126 pixels
+__device__ __forceinline__ PairSub pair2_sub(const ConvArgs& a, int u) { return pair_sub(a, u); }
+
+// Writes this lane's pixel (32 fp16 channels = 64 B) of an x_k row into a hand-off slot: pixel index `px` of box row `r`, in the
+// SWIZZLE_64B layout of a TMA box (16 B unit u of the 64 B pixel row at unit u ^ ((offset >> 7) & 3); slots are 512 B aligned).
+__device__ __forceinline__ void hand_store(uint32_t slot_s, int r, int px, const uint4& h0, const uint4& h1, const uint4& h2, const uint4& h3) {
+    const uint32_t o = static_cast<uint32_t>(r * 130 + px) * 64u;
+    const uint32_t sw = (o >> 7) & 3u;
+    ptx::sts128(slot_s + o + ((0u ^ sw) << 4), h0);
+    ptx::sts128(slot_s + o + ((1u ^ sw) << 4), h1);
+    ptx::sts128(slot_s + o + ((2u ^ sw) << 4), h2);
+    ptx::sts128(slot_s + o + ((3u ^ sw) << 4), h3);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Pair2::kThreads, 1)
+conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
+    using T = PairTraits<32>;
+    constexpr int N = 32;
+    constexpr uint32_t P = Pair2::P;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t s_bars[2 * kPairMaxSlots + 4 * P + 2 * Pair2::kHand + 1];
+    __shared__ uint32_t s_tmem_slot;
+    __shared__ __align__(16) float s_bias[2][N];
+    uint64_t* full = s_bars;                    // leader: both CTAs' boxes of a TMA slot have landed
+    uint64_t* empty = full + kPairMaxSlots;     // both: the MMAs reading the slot have retired (multicast commit)
+    uint64_t* tfull = empty + kPairMaxSlots;    // both: [layer][P] logical ring position complete (multicast commit)
+    uint64_t* tempty = tfull + 2 * P;           // leader: [layer][P] ring position drained and re-initialised in BOTH CTAs
+    uint64_t* hfull = tempty + 2 * P;           // leader: both x_k rows of a hand-off slot written in BOTH CTAs
+    uint64_t* hempty = hfull + Pair2::kHand;    // both: the MMAs reading the hand-off slot have retired (multicast commit)
+    uint64_t* wfull = hempty + Pair2::kHand;
+    const int nslots = a.nstages;
+    const int nchA = a.nchunks, nchB = a.nchunks + 1;
+    uint8_t* wB = smem + nchA * T::kBHalf;
+    uint8_t* hand0 = wB + nchB * T::kBHalf;
+    uint8_t* slot0 = hand0 + Pair2::kHand * T::kASlot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const long long t_start = clock64();
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPairMaxSlots; ++i) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], 1);
+        }
+        for (uint32_t i = 0; i < 2 * P; ++i) {
+            ptx::mbar_init(&tfull[i], kMmaWarps);   // both issuer warps commit (multicast) their MMAs of the row
+            ptx::mbar_init(&tempty[i], 8);          // four lane-quarter warps in each of the two CTAs
+        }
+        for (int i = 0; i < Pair2::kHand; ++i) {
+            ptx::mbar_init(&hfull[i], 16);          // two rows x four lane-quarter warps x two CTAs
+            ptx::mbar_init(&hempty[i], 1);
+        }
+        ptx::mbar_init(wfull, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == T::kEpi) {
+        if (lane == 0) ptx::prefetch_tmap(&tmap);
+        __syncwarp();
+        ptx::tmem_alloc_pair<512>(&s_tmem_slot);
+    }
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+        const float* b = i < N ? a.bias : a.bias2;
+        s_bias[i / N][i % N] = b ? b[i % N] : 0.f;
+    }
+    // hand-off slots: the halo pixels 0 and 129 of each row are never written by the epilogue; they only reach discarded
+    // outputs, but must not hold NaN patterns from a previous kernel
+    for (int i = threadIdx.x; i < Pair2::kHand * T::kASlot / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(hand0)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = s_tmem_slot;
+    if (warp == T::kEpi && lane == 0) {
+        // this CTA's halves of both layers' weight rows; weights are never written by a kernel: fetch before the dependency wait
+        const __half* wpa = a.wpack + (static_cast<size_t>(rank) * nchA) * (T::kBHalf / 2);
+        const __half* wpb = a.wpack2 + (static_cast<size_t>(rank) * nchB) * (T::kBHalf / 2);
+        ptx::mbar_expect_tx(wfull, (nchA + nchB) * T::kBHalf);
+        for (int c = 0; c < nchA; ++c) ptx::bulk_load(smem + c * T::kBHalf, wpa + static_cast<size_t>(c) * (T::kBHalf / 2), T::kBHalf, wfull);
+        for (int c = 0; c < nchB; ++c) ptx::bulk_load(wB + c * T::kBHalf, wpb + static_cast<size_t>(c) * (T::kBHalf / 2), T::kBHalf, wfull);
+    }
+    if (warp < T::kEpi) {
+        // ring blocks start as the bias row of their layer, mirror blocks as zero; every MMA accumulates
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+#pragma unroll
+        for (int L = 0; L < 2; ++L) {
+            float bz[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bz[j] = s_bias[L][j];
+            for (uint32_t blk = warp >> 2; blk < static_cast<uint32_t>(Pair2::kPhys); blk += T::kGroups) {
+                const uint32_t t = tmem_base + lane_base + L * Pair2::kRingCols + blk * N;
+                if (blk < P) ptx::tmem_st32(t, bz);
+                else ptx::tmem_st32_zero(t);
+            }
+        }
+        ptx::tmem_st_wait();
+    }
+    ptx::mbar_wait(wfull, 0);
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // both CTAs: barriers initialised, TMEM initialised, weight halves resident
+    ptx::tc_fence_after();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const int num_items = (a.tiles_x * a.nbands + 1) >> 1;
+    const int cluster_id = static_cast<int>(blockIdx.x) >> 1, nclusters = static_cast<int>(gridDim.x) >> 1;
+
+    if (warp == T::kEpi) {
+        // ===================== TMA producer: this CTA's strip; bytes counted on the leader's barrier =====================
+        if (lane == 0) {
+            const uint32_t lead_full = ptx::map_to_rank(&full[0], 0);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int item = cluster_id; item < num_items; item += nclusters) {
+                const PairSub me = pair2_sub(a, 2 * item + static_cast<int>(rank));
+                const int xc = me.sx * Pair2::kStrip - 2;  // box column 0: one pixel left of the strip's first (halo) pixel
+                Pair2Iter it;
+                it.init((pair_rows(a, item) + 3) & ~1, nchA);
+                for (; !it.done(); it.next()) {
+                    if (it.hand()) continue;
+                    // A's input rows start one row above B's: A computes the band plus a halo row on either side
+                    const int yrow = it.part == 0 ? me.y0 - 2 + 2 * it.s : me.y0 - 1 + 2 * (it.s - Pair2::kLag);
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
+                    const int ch0 = a.cin_off + it.c * T::KC;
+                    ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0, xc, yrow,
+                                          a.in_cstride == 32 ? ch0 >> 5 : 0);
+                    if (++s == nslots) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp > T::kEpi) {
+        // ===================== MMA issuers: leader only; two warps alternate units of boxes as in K3 =====================
+        if (rank == 0) {
+            const int mw = warp - (T::kEpi + 1);
+            const int unit = a.unit < 1 ? 1 : a.unit;
+            int s = 0;           // TMA slot ring
+            uint32_t ph = 0;
+            uint32_t hcnt = 0;   // hand-off boxes consumed so far (slot = hcnt % kHand)
+            int gunit = 0;
+            uint32_t g0A = 0, g0B = 0;  // logical rows started before the current item, per layer
+            for (int item = cluster_id; item < num_items; item += nclusters) {
+                const int nin2B = (pair_rows(a, item) + 3) & ~1, nin2A = nin2B + 2;
+                Pair2Iter it;
+                it.init(nin2B, nchA);
+                const int nb = it.boxes();
+                for (int n = 0; n < nb; n += unit, ++gunit) {
+                    const int cnt = nb - n < unit ? nb - n : unit;
+                    const bool mine = (gunit & 1) == mw;
+                    if (mine) {
+                        Pair2Iter w = it;
+                        int ss = s;
+                        uint32_t pp = ph, hh = hcnt;
+                        for (int i = 0; i < cnt; ++i, w.next()) {
+                            if (w.hand()) {
+                                ptx::mbar_wait(&hfull[hh % Pair2::kHand], (hh / Pair2::kHand) & 1u);
+                                ++hh;
+                            } else {
+                                ptx::mbar_wait(&full[ss], pp);
+                                if (++ss == nslots) { ss = 0; pp ^= 1; }
+                            }
+                            if (w.c == 0) {
+                                // logical rows first touched by this row pair: ga + 2, ga + 3 (and ga, ga + 1 at the top of an item)
+                                const int jj = 2 * w.pair_index();
+                                const uint32_t ga = (w.part == 0 ? g0A : g0B) + jj;
+                                uint64_t* te = tempty + w.part * P;
+                                for (uint32_t gl = (jj == 0 ? ga : ga + 2); gl < ga + 4; ++gl)
+                                    ptx::mbar_wait(&te[gl % P], ((gl / P) & 1u) ^ 1u);
+                            }
+                        }
+                        ptx::tc_fence_after();
+                        if (gunit > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+                    }
+                    if (ptx::elect_one()) {
+                        Pair2Iter w = it;
+                        int ss = s;
+                        uint32_t hh = hcnt;
+                        for (int i = 0; i < cnt; ++i, w.next()) {
+                            const int L = w.part;
+                            const int jj = 2 * w.pair_index();
+                            const uint32_t ga = (L == 0 ? g0A : g0B) + jj;
+                            const uint32_t s0 = ga % P, s1 = (ga + 1) % P;
+                            const uint32_t tb = tmem_base + L * Pair2::kRingCols;
+                            const bool hand = w.hand();
+                            if (mine) {
+                                const uint8_t* aslot = hand ? hand0 + (hh % Pair2::kHand) * T::kASlot : slot0 + ss * T::kASlot;
+                                const uint8_t* bw = (L == 0 ? smem : wB) + w.c * T::kBHalf;
+                                pair_issue_box<N>(tb + s0 * N, tb + s1 * N, ptx::smem_u32(aslot) >> 4, ptx::smem_u32(bw) >> 4);
+                                ptx::umma_commit_pair(hand ? &hempty[hh % Pair2::kHand] : &empty[ss]);
+                            }
+                            if (w.last_chunk()) {
+                                uint64_t* tf = tfull + L * P;
+                                ptx::umma_commit_pair(&tf[s0]);
+                                ptx::umma_commit_pair(&tf[s1]);
+                                if (jj + 2 >= (L == 0 ? nin2A : nin2B)) {
+                                    ptx::umma_commit_pair(&tf[(ga + 2) % P]);
+                                    ptx::umma_commit_pair(&tf[(ga + 3) % P]);
+                                }
+                            }
+                            if (hand) ++hh;
+                            else if (++ss == nslots) ss = 0;
+                        }
+                    }
+                    __syncwarp();
+                    if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");
+                    for (int i = 0; i < cnt; ++i, it.next()) {
+                        if (it.hand()) ++hcnt;
+                        else if (++s == nslots) { s = 0; ph ^= 1; }
+                    }
+                }
+                g0A += nin2A + 2;
+                g0B += nin2B + 2;
+            }
+            // the last unit's arrive has no matching sync: consume it so no named barrier is left half-arrived
+            if (gunit > 0 && (gunit & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs): warp % 4 = TMEM lane quarter, warp / 4 = row group =====================
+        const int quarter = warp & 3;
+        const uint32_t rgrp = warp >> 2;
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t lead_tempty = ptx::map_to_rank(&tempty[0], 0);
+        const uint32_t lead_hfull = ptx::map_to_rank(&hfull[0], 0);
+        const uint32_t hand_s = ptx::smem_u32(hand0);
+        const int local = quarter * 32 + lane;                 // pixel of the 128-pixel MMA tile
+        const bool owned_col = local >= 1 && local <= Pair2::kStrip;
+        const float slope = a.slope;
+        uint32_t g0A = 0, g0B = 0, hbase = 0;  // hbase: hand-off row pairs filled before the current item
+        for (int item = cluster_id; item < num_items; item += nclusters) {
+            const PairSub me = pair2_sub(a, 2 * item + static_cast<int>(rank));
+            const int y0 = me.y0, nrow = me.nrow;
+            const int nin2B = (pair_rows(a, item) + 3) & ~1, nin2A = nin2B + 2;
+            const int x = me.sx * Pair2::kStrip - 1 + local;
+            const bool x_in = x >= 0 && x < a.W;
+            bool xgap = false;
+            for (int j = 0; j < a.ngx; ++j) xgap |= (x_in && (x >> a.gshift) == a.gx[j]);
+            const int nA2 = nin2A >> 1, nB2 = nin2B >> 1;
+            const int S = nB2 + Pair2::kLag;
+            // one logical row of layer L: drain, hand the ring position back, then (real rows) activation -> fp16 -> hand-off / global
+            auto do_row = [&](int L, int l) {
+                const uint32_t gl = (L == 0 ? g0A : g0B) + l;
+                const uint32_t m = gl % P;
+                ptx::mbar_wait(&tfull[L * P + m], (gl / P) & 1u);
+                ptx::tc_fence_after();
+                const uint32_t t_main = tmem_base + lane_base + L * Pair2::kRingCols + m * N;
+                const uint32_t t_mir = m < 2 ? tmem_base + lane_base + L * Pair2::kRingCols + (P + m) * N : 0xffffffffu;
+                float v[32];
+                if (t_mir != 0xffffffffu) {
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld32_issue(t_main, r0);
+                    ptx::tmem_ld32_issue(t_mir, r1);
+                    ptx::tmem_ld32_wait(r0);
+                    ptx::tmem_ld32_wait(r1);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                } else {
+                    ptx::tmem_ld32(t_main, v);
+                }
+                pair_release<N>(t_main, t_mir, s_bias[L], lane, lead_tempty + (L * P + m) * 8);
+                // image row of this logical row: A's band starts one row above B's
+                const int y = L == 0 ? y0 - 3 + l : y0 - 2 + l;
+                const int jB = l - 2;  // layer A: the B input row this x_k row is
+                const bool handoff = L == 0 && jB >= 0 && jB < nin2B;
+                const bool real = l >= 2 && l < (L == 0 ? nrow + 4 : nrow + 2);
+                if (!handoff && !real) return;
+                bool zero = !x_in || xgap || y < 0 || y >= a.H || !real;
+                if (!zero)
+                    for (int j = 0; j < a.ngy; ++j) zero |= ((y >> a.gshift) == a.gy[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = zero ? 0.f : fmaxf(v[j], v[j] * slope);
+                const uint4 h0 = pack8(v), h1 = pack8(v + 8), h2 = pack8(v + 16), h3 = pack8(v + 24);
+                if (handoff) {
+                    const uint32_t f = hbase + static_cast<uint32_t>(jB >> 1);
+                    const uint32_t q = f % Pair2::kHand;
+                    ptx::mbar_wait(&hempty[q], ((f / Pair2::kHand) & 1u) ^ 1u);
+                    hand_store(hand_s + q * T::kASlot, jB & 1, 1 + local, h0, h1, h2, h3);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(lead_hfull + q * 8);
+                }
+                // global store: only rows of the band itself (A's halo rows belong to the neighbouring bands) and owned columns
+                const bool in_band = L == 0 ? (l >= 3 && l < nrow + 3) : real;
+                if (in_band && owned_col && x < a.W && !(a.flags & FLAG_SKIP_B)) {
+                    const size_t p = static_cast<size_t>(y) * a.W + x;
+                    __half* o = a.out + chan_off(p, a.out_cstride, a.out_pstride, L == 0 ? a.out_coff : a.out_coff2);
+                    ptx::stg256(o, h0, h1);
+                    ptx::stg256(o + 16, h2, h3);
+                }
+            };
+            for (int s = 0; s < S; ++s) {
+                if (s < nA2) {
+                    do_row(0, 2 * s + static_cast<int>(rgrp));
+                    if (s == nA2 - 1) do_row(0, nin2A + static_cast<int>(rgrp));
+                }
+                const int b = s - Pair2::kLag;
+                if (b >= 0 && b < nB2) {
+                    do_row(1, 2 * b + static_cast<int>(rgrp));
+                    if (b == nB2 - 1) do_row(1, nin2B + static_cast<int>(rgrp));
+                }
+            }
+            g0A += nin2A + 2;
+            g0B += nin2B + 2;
+            hbase += static_cast<uint32_t>(nB2);
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // the peer may still be read (operands) or signalled (barriers) until both are done
+    if (warp == T::kEpi) {
+        __syncwarp();
+        ptx::tmem_dealloc_pair<512>(tmem_base);
+    }
+    if (a.dbg_cycles && threadIdx.x == 0) a.dbg_cycles[blockIdx.x] = clock64() - t_start;
+}
+
+}  // namespace vr

@@ -57,6 +57,11 @@ struct ConvArgs {
     // conv_first feeds both the trunk skip (`feat`) and the first dense block's x slot from one launch
     __half* out2;
     int out2_cstride;
+    // K4 (conv3x3_pair2_sm100.cuh): the NEXT layer of the dense block, run in the same launch two row pairs behind this one.
+    // It reads the same source planes plus this layer's output (handed over through shared memory) and writes `out_coff2`.
+    const __half* wpack2;  // K3 weight halves of the second layer, nchunks + 1 chunks
+    const float* bias2;
+    int out_coff2;
     // Chunk-planar tensors: a tensor with cstride == 32 stores channels [32k, 32k+32) as plane k, [H][W][32] fp16, planes
     // `pstride` elements apart (every TMA box row and every output row is then contiguous; the interleaved [H][W][C] form
     // costs the 32-channel layers 16..52 %). Any other cstride is the interleaved form (pstride unused).

@@ -1,7 +1,7 @@
 // Host side of the convolution kernels K1 / K2 / K3: weight repacking into the swizzled shared-memory images, TMA
 // tensor-map construction, kernel selection and launch. Kernels: conv3x3_sm100.cuh (K1), conv3x3_roll_sm100.cuh (K2),
 // conv3x3_pair_sm100.cuh (K3, the default for 32 / 64 output channels).
-#include "conv3x3_pair_sm100.cuh"
+#include "conv3x3_pair2_sm100.cuh"
 #include "vr_common.h"
 
 #include <cstdlib>
@@ -366,6 +366,51 @@ static int launch_pair(Device& dev, const CUtensorMap& tm, ConvArgs a, const Con
     return 0;
 }
 
+// K4: two 32-channel dense-block layers in one launch. returns 1 when the pair does not fit, 0 on launch, < 0 on error
+static int launch_pair2(Device& dev, const CUtensorMap& tm, ConvArgs a, const ConvWeights& wa, const ConvWeights& wb) {
+    using T = PairTraits<32>;
+    if (!wa.wpair || !wb.wpair || wa.cout != 32 || wb.cout != 32 || wb.nchunks != wa.nchunks + 1) return 1;
+    const int w_bytes = (wa.nchunks + wb.nchunks) * T::kBHalf;
+    int nslots = (Pair2::kBudget - w_bytes - Pair2::kHand * T::kASlot) / T::kASlot;
+    if (nslots < Pair2::kMinSlots) return 1;
+    if (nslots > kPairMaxSlots) nslots = kPairMaxSlots;
+    auto kern = conv3x3_pair2_kernel;
+    static bool attr_done[64] = {};
+    if (!attr_done[dev.ordinal & 63]) {
+        VR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2::kBudget + 1024), dev.err);
+        attr_done[dev.ordinal & 63] = true;
+    }
+    a.nsplit = 1;
+    a.wpack = wa.wpair;
+    a.wpack2 = wb.wpair;
+    a.bias2 = wb.bias;
+    a.nstages = nslots;
+    a.unit = dev.pair_unit > 0 && dev.pair_unit <= 3 ? dev.pair_unit : 2;
+    if (a.unit > nslots) a.unit = nslots;
+    a.tiles_x = (a.W + Pair2::kStrip - 1) / Pair2::kStrip;
+    const int max_clusters = dev.sm_count / 2;
+    choose_bands(a.tiles_x, a.y_end - a.y_begin, 2 * max_clusters, &a.band, &a.nbands);
+    const int items = (a.tiles_x * a.nbands + 1) / 2;
+    int nclusters = items < max_clusters ? items : max_clusters;
+    if (dev.max_ctas > 1 && nclusters > dev.max_ctas / 2) nclusters = dev.max_ctas / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nclusters);
+    cfg.blockDim = dim3(Pair2::kThreads);
+    cfg.dynamicSmemBytes = w_bytes + (Pair2::kHand + nslots) * T::kASlot + 1024;
+    cfg.stream = dev.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = dev.use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, a), dev.err);
+    dev.launches++;
+    dev.conv_launches++;
+    return 0;
+}
+
+bool conv_supports_pair2(const Device& dev) { return dev.fuse_pairs && dev.planar && (dev.rolling & 8); }
+
 bool conv_supports_out2(const Device& dev, int cout) {
     return dev.epi_direct && ((cout == 32 && (dev.rolling & 8)) || (cout == 64 && (dev.rolling & 16)));
 }
@@ -383,6 +428,7 @@ void read_conv_env(Device& dev) {
     getb("VR_PAIRPAD", &dev.pair_pad);
     geti("VR_MAX_CTAS", &dev.max_ctas);
     geti("VR_EPI_DIRECT", &dev.epi_direct);
+    geti("VR_K4", &dev.fuse_pairs);
     geti("VR_EARLY64", &dev.early64);
     geti("VR_UNIT", &dev.pair_unit);
     geti("VR_L2HINT", &dev.l2_hint);
@@ -435,6 +481,7 @@ int run_conv(Device& dev, const ConvCall& c) {
     a.out_coff = c.out_coff;
     a.out2 = c.out2;
     a.out2_cstride = c.out2_cstride;
+    a.out_coff2 = c.out_coff2;
     a.cout = w.cout;
     a.res1 = c.res1;
     a.res1_cstride = c.res1_cstride;
@@ -488,6 +535,24 @@ int run_conv(Device& dev, const ConvCall& c) {
     if (c.out_mode == OUT_PS4 && w.npad != 48) {
         set_error(dev.err, "run_conv: pixel-shuffle output needs cout == 48");
         return -1;
+    }
+    if (c.w2) {
+        // K4: this layer and the dense block's next one in one launch (chunk-planar tensors, full row range, LeakyReLU, no residuals)
+        if (c.nlayers != 1 || c.out_mode != OUT_NHWC || c.in_cstride != 32 || c.out_cstride != 32 || c.res1 || c.res2 || c.out2 ||
+            c.act != ACT_LRELU || c.slope < 0.f || c.slope > 1.f || c.dys || c.dxs || c.omul > 1 || a.y_begin != 0 || a.y_end != c.H ||
+            c.out_coff % 32 != 0 || c.out_coff2 % 32 != 0 || w.kc != 32) {
+            set_error(dev.err, "run_conv: this layer pair is not a K4 shape");
+            return -1;
+        }
+        CUtensorMap tm2;
+        rc = make_act_tmap(dev, c.in, c.in_cstride, c.W, c.H, 0, w.kc, c.in_planes, c.in_pstride, &tm2);  // two input rows
+        if (rc) return rc;
+        rc = launch_pair2(dev, tm2, a, w, *c.w2);
+        if (rc == 1) {
+            set_error(dev.err, "run_conv: the layer pair does not fit K4");
+            return -1;
+        }
+        return rc;
     }
     const bool roll_shape = c.out_mode == OUT_NHWC && c.nlayers == 1 && !c.dys && !c.dxs && c.rows == 0 && w.kc == 32 &&
                             (w.cout == 32 || w.cout == 64);

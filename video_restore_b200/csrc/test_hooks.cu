@@ -192,6 +192,113 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     return rc;
 }
 
+// K4 hook: two consecutive dense-block layers in one launch. x [H][W][cin] (cin % 32 == 0), layer A cin -> 32, layer B
+// (cin + 32) -> 32, both + bias + LeakyReLU(slope); yA / yB [H][W][32]. Tensors are the network's chunk-planar dense-block
+// buffer (cin / 32 + 2 planes). iters > 1: average ms per launch in *ms. flags: VR_MAX_CTAS etc. through the environment.
+extern "C" int vr_conv_pair2_test(int32_t device, int32_t H, int32_t W, int32_t cin, const float* x, const float* wa, const float* ba,
+                                  const float* wb, const float* bb, float slope, float* ya, float* yb, int32_t iters, float* ms,
+                                  const int32_t* gaps_x, int32_t ngx, const int32_t* gaps_y, int32_t ngy) {
+    if (!x || !wa || !wb || !ya || !yb || H <= 0 || W <= 0 || cin <= 0 || cin % 32 != 0 || ngx > 7 || ngy > 7) {
+        set_error(nullptr, "vr_conv_pair2_test: bad arguments");
+        return VR_E_INVALID;
+    }
+    ScopedDev sd(device);
+    if (!sd.ok) return VR_E_NODEVICE;
+    Device& dev = sd.dev;
+    const size_t px = static_cast<size_t>(H) * W;
+    const int planes = cin / 32 + 2;
+    ConvWeights cwa, cwb;
+    int rc = pack_conv_weights(dev, wa, ba, nullptr, cin, 32, &cwa);
+    if (rc) return rc;
+    rc = pack_conv_weights(dev, wb, bb, nullptr, cin + 32, 32, &cwb);
+    if (rc) return rc;
+    std::vector<__half> hx = to_half_padded(x, px, cin, cin, true);
+    constexpr size_t kGuard = 8192;
+    const size_t bytes = static_cast<size_t>(planes) * px * 32 * sizeof(__half);
+    uint8_t* raw = nullptr;
+    VR_CUDA_CHECK(cudaMalloc(&raw, bytes + 2 * kGuard), dev.err);
+    VR_CUDA_CHECK(cudaMemset(raw, 0xA5, bytes + 2 * kGuard), dev.err);
+    __half* buf = reinterpret_cast<__half*>(raw + kGuard);
+    // the two output planes start as NaN patterns: every element the kernel owns must be written
+    VR_CUDA_CHECK(cudaMemset(buf + static_cast<size_t>(cin / 32) * px * 32, 0xFF, 2 * px * 32 * sizeof(__half)), dev.err);
+    VR_CUDA_CHECK(cudaMemcpy(buf, hx.data(), hx.size() * sizeof(__half), cudaMemcpyHostToDevice), dev.err);
+    VR_CUDA_CHECK(cudaDeviceSynchronize(), dev.err);
+    ConvCall c;
+    c.in = buf;
+    c.in_cstride = 32;
+    c.in_planes = planes;
+    c.in_pstride = static_cast<long long>(px) * 32;
+    c.H = H;
+    c.W = W;
+    c.w = &cwa;
+    c.w2 = &cwb;
+    c.act = ACT_LRELU;
+    c.slope = slope;
+    c.out = buf;
+    c.out_cstride = 32;
+    c.out_pstride = static_cast<long long>(px) * 32;
+    c.out_coff = cin;
+    c.out_coff2 = cin + 32;
+    c.ngx = ngx;
+    c.ngy = ngy;
+    for (int i = 0; i < ngx; ++i) c.gx[i] = gaps_x[i];
+    for (int i = 0; i < ngy; ++i) c.gy[i] = gaps_y[i];
+    const int n = iters > 0 ? iters : 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    rc = run_conv(dev, c);
+    if (rc == 0) {
+        cudaEventRecord(e0, dev.stream);
+        for (int i = 1; i < n && rc == 0; ++i) rc = run_conv(dev, c);
+        cudaEventRecord(e1, dev.stream);
+    }
+    cudaError_t se = cudaStreamSynchronize(dev.stream);
+    if (rc == 0 && se != cudaSuccess) {
+        set_error(dev.err, std::string("pair2 kernel failed: ") + cudaGetErrorString(se));
+        rc = VR_E_CUDA;
+    }
+    if (rc == 0) {
+        if (ms) {
+            float t = 0.f;
+            if (n > 1) {
+                cudaEventElapsedTime(&t, e0, e1);
+                t /= (n - 1);
+            }
+            *ms = t;
+        }
+        std::vector<__half> hy(2 * px * 32);
+        cudaMemcpy(hy.data(), buf + static_cast<size_t>(cin / 32) * px * 32, hy.size() * sizeof(__half), cudaMemcpyDeviceToHost);
+        for (size_t p = 0; p < px; ++p)
+            for (int ch = 0; ch < 32; ++ch) {
+                ya[p * 32 + ch] = __half2float(hy[p * 32 + ch]);
+                yb[p * 32 + ch] = __half2float(hy[(px + p) * 32 + ch]);
+            }
+        std::vector<uint8_t> g0(kGuard), g1(kGuard);
+        cudaMemcpy(g0.data(), raw, kGuard, cudaMemcpyDeviceToHost);
+        cudaMemcpy(g1.data(), raw + kGuard + bytes, kGuard, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < kGuard; ++i)
+            if (g0[i] != 0xA5 || g1[i] != 0xA5) {
+                set_error(dev.err, "pair2 kernel wrote outside its tensor (guard band damaged)");
+                rc = VR_E_CUDA;
+                break;
+            }
+        // the source planes must be untouched
+        std::vector<__half> back(hx.size());
+        cudaMemcpy(back.data(), buf, back.size() * sizeof(__half), cudaMemcpyDeviceToHost);
+        if (rc == 0 && std::memcmp(back.data(), hx.data(), hx.size() * sizeof(__half)) != 0) {
+            set_error(dev.err, "pair2 kernel modified its source planes");
+            rc = VR_E_CUDA;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(raw);
+    free_conv_weights(&cwa);
+    free_conv_weights(&cwb);
+    return rc;
+}
+
 extern "C" int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t rows,
                                 int32_t flags, int32_t iters, float* ms_out) {
     ScopedDev sd(device);

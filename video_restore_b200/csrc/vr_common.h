@@ -52,6 +52,10 @@ struct ConvCall {
     int out_cstride = 0, out_coff = 0;
     __half* out2 = nullptr;  // optional second destination (K3 direct epilogue only), same channel offset / plane distance
     int out2_cstride = 0;
+    // K4: the dense block's next layer fused into this launch (32 -> 32 output channels, LeakyReLU, chunk-planar tensors):
+    // it reads the same source prefix plus this layer's 32 output channels and writes channel slice out_coff2
+    const ConvWeights* w2 = nullptr;
+    int out_coff2 = 0;
     long long out_pstride = 0, res1_pstride = 0, res2_pstride = 0;  // plane distances (cstride == 32 tensors)
     const __half* res1 = nullptr;
     int res1_cstride = 0, res1_coff = 0;
@@ -114,6 +118,7 @@ struct Device {
     // VR_EARLY64 = 0 / 1 / 2 when a 64-channel row's ring position goes back (ConvArgs::early64); VR_UNIT boxes per issuer
     // hand-over (0 = automatic); VR_L2HINT / VR_L2FRAC cache-policy experiments (ConvArgs::l2_hint)
     int epi_direct = 1;
+    int fuse_pairs = 1;   // VR_K4=0: conv1+conv2 / conv3+conv4 of a dense block as separate K3 launches (A/B runs)
     int early64 = 2;
     int pair_unit = 0;
     int l2_hint = 0;
@@ -126,6 +131,7 @@ int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const
                       ConvWeights* out, int kc = 0);  // kc = 0: default (env VR_KC or 32)
 void free_conv_weights(ConvWeights* w);
 int run_conv(Device& dev, const ConvCall& c);
+bool conv_supports_pair2(const Device& dev);  // K4 is enabled (VR_K4, default on) and its prerequisites (K3, planar tensors) hold
 bool conv_supports_out2(const Device& dev, int cout);  // the configured kernel for a `cout`-channel NHWC layer takes ConvCall::out2
 // reads every conv-related environment switch into `dev` (called when a handle / test device is created, so that one
 // process can run several configurations)
