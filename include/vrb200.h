@@ -169,10 +169,14 @@ int vr_conv3x3_test(vr_conv_test* t);
 const char* vr_global_error(void);
 
 /* K4 test / bench hook: two consecutive 32-channel dense-block layers (cin -> 32, cin + 32 -> 32, bias + LeakyReLU) in ONE launch
- * over a chunk-planar buffer, x [H][W][cin] (cin % 32 == 0), ya / yb [H][W][32]; optional tile-atlas gap columns / rows. */
+ * over a chunk-planar buffer, x [H][W][cin] (cin % 32 == 0), ya / yb [H][W][32]; optional tile-atlas gap columns / rows;
+ * flags: measurement ablations -- 4 skip MMA, 8 hand-off without data, 16 no global stores. */
 int vr_conv_pair2_test(int32_t device, int32_t H, int32_t W, int32_t cin, const float* x, const float* wa, const float* ba,
                        const float* wb, const float* bb, float slope, float* ya, float* yb, int32_t iters, float* ms,
-                       const int32_t* gaps_x, int32_t ngx, const int32_t* gaps_y, int32_t ngy);
+                       const int32_t* gaps_x, int32_t ngx, const int32_t* gaps_y, int32_t ngy, int32_t flags);
+
+/* Wait-cycle profile of the last vr_conv_pair2_test launch (cluster 0's leader CTA): 64 counters, see conv3x3_pair2_sm100.cuh. */
+void vr_pair2_profile(int64_t* out64);
 
 /* Device-resident conv benchmark on zero-copy synthetic data: returns average ms per launch. */
 int vr_conv3x3_bench(int32_t device, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t rows,

@@ -345,6 +345,41 @@ def test_enhancement_chain_composition(gpu_lib):
     gpu.close()
 
 
+def test_enhancement_chain_vectorised_fused_temporal(gpu_lib):
+    """Frame sizes that take the vectorised kernels (HR width / 8 a multiple of 16): from the second frame on the temporal blend
+    is fused into CLAHE's apply pass (one kernel writes the un-blended frame AND the blended one) -- still bit-exact against the
+    oracle filters applied to the GPU's own upscaled frames, including the temporal state it leaves behind."""
+    from oracle import filters as OF
+    from video_restore_b200.restorer import FrameOpts
+
+    gpu, _ = _pair("RealESRGAN_x4_v3", 64, 10)
+    frames = [synth_frame(32, 64, seed=6, index=i) for i in range(4)]
+    opts = FrameOpts(denoise=True, sharpen=0.5, clahe=True, temporal=True, temporal_tau=40.0)
+    ups = [OF.clahe_bgr(OF.unsharp_mask(gpu.process_frame(f, FrameOpts(denoise=True)), 0.5)) for f in frames]
+    gpu.temporal_reset()
+    n0 = gpu.launch_count
+    outs = []
+    per_frame = []
+    for f in frames:
+        outs.append(gpu.process_frame(f, opts))
+        per_frame.append(gpu.launch_count - n0)
+        n0 = gpu.launch_count
+    assert np.array_equal(outs[0], ups[0])
+    for t in (1, 2, 3):
+        assert np.array_equal(outs[t], OF.temporal_blend(ups[t], ups[t - 1], 0.2, 40.0)), t
+        assert not np.array_equal(outs[t], ups[t])            # the blend really acts on this clip
+    assert per_frame[1] == per_frame[2] == per_frame[3]      # frame 0: temporal passes through (a copy); then one fused kernel
+    assert np.array_equal(gpu.temporal_get_prev(*ups[3].shape[:2]), ups[3])
+    # sharpen off: CLAHE + temporal alone take the same fused pass
+    gpu.temporal_reset()
+    o2 = FrameOpts(clahe=True, temporal=True, temporal_tau=40.0)
+    raw = [gpu.process_frame(f) for f in frames[:2]]
+    got = [gpu.process_frame(f, o2) for f in frames[:2]]
+    e = [OF.clahe_bgr(r) for r in raw]
+    assert np.array_equal(got[0], e[0]) and np.array_equal(got[1], OF.temporal_blend(e[1], e[0], 0.2, 40.0))
+    gpu.close()
+
+
 def test_device_path_equals_host_path_and_is_deterministic(gpu_lib):
     import torch
 

@@ -83,7 +83,8 @@ SIGNATURES = {
     "vr_conv3x3_test": (C.c_int, [C.POINTER(VrConvTest)]),
     "vr_conv_pair2_test": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_void_p,
-                                     C.c_int32, C.c_void_p, C.c_int32]),
+                                     C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "vr_pair2_profile": (None, [C.c_void_p]),
     "vr_global_error": (C.c_char_p, []),
     "vr_conv3x3_bench": (C.c_int, [C.c_int32] * 8 + [C.POINTER(C.c_float)]),
     "vr_last_conv_cycles": (C.c_int64, []),
@@ -153,7 +154,7 @@ def conv3x3(x, weight, bias=None, act=0, slope=0.2, prelu=None, res1=None, s1=1.
     return y, float(t.ms)
 
 
-def conv_pair2(x, wa, ba, wb, bb, slope=0.2, iters=1, gaps_x=(), gaps_y=(), device=0):
+def conv_pair2(x, wa, ba, wb, bb, slope=0.2, iters=1, gaps_x=(), gaps_y=(), device=0, flags=0):
     """K4 hook: x [H,W,Cin] (Cin % 32 == 0); layer A Cin -> 32, layer B Cin + 32 -> 32 (input = concat(x, yA)), both with bias and
     LeakyReLU. Returns (yA, yB, ms)."""
     lib = load()
@@ -166,8 +167,22 @@ def conv_pair2(x, wa, ba, wb, bb, slope=0.2, iters=1, gaps_x=(), gaps_y=(), devi
     ms = C.c_float(0)
     ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     check(lib.vr_conv_pair2_test(device, H, W, cin, ptr(x), ptr(wa), ptr(ba), ptr(wb), ptr(bb), slope, ptr(ya), ptr(yb), iters,
-                                 C.byref(ms), ptr(gx) if gx.size else None, gx.size, ptr(gy) if gy.size else None, gy.size))
+                                 C.byref(ms), ptr(gx) if gx.size else None, gx.size, ptr(gy) if gy.size else None, gy.size, flags))
     return ya, yb, float(ms.value)
+
+
+def pair2_profile():
+    """{name: cycles} of cluster 0's leader CTA in the last conv_pair2 launch."""
+    a = np.zeros(64, np.int64)
+    load().vr_pair2_profile(a.ctypes.data_as(C.c_void_p))
+    names = {0: "producer.wait_empty", 1: "producer.total"}
+    for mw in (0, 1):
+        for i, n in enumerate(("wait_full", "wait_tempty", "wait_hfull", "handover", "issue", "total", "units")):
+            names[10 + mw * 8 + i] = f"issuer{mw}.{n}"
+    for g in (0, 1):
+        for i, n in enumerate(("wait_tfull", "wait_hempty", "rows", "total")):
+            names[30 + g * 4 + i] = f"epilogue{g}.{n}"
+    return {n: int(a[i]) for i, n in names.items()}
 
 
 def conv3x3_bench(H, W, cin, cout, rows=0, flags=0, iters=20, device=0) -> float:

@@ -564,6 +564,10 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
             VR_TRY(launch_unsharp(dev, cur_ptr(), hr_stride, sH, sW, dst, dstride, o.sharpen));
             if (!last) cur ^= 1;
         }
+        const float alpha = o.temporal_alpha > 0 ? o.temporal_alpha : 0.2f;
+        const float tau = o.temporal_tau > 0 ? o.temporal_tau : 12.f;
+        const bool prev_ok = h->has_prev && h->prev_h == sH && h->prev_w == sW;
+        bool temporal_done = false;
         if (o.clahe) {
             const bool last = !o.temporal;
             uint8_t* dst = d_out;
@@ -576,14 +580,19 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
             const int g = o.clahe_grid > 0 ? o.clahe_grid : 8;
             VR_TRY(ensure(h, h->clahe_hist, static_cast<size_t>(g) * g * 256 * 4));
             VR_TRY(ensure(h, h->clahe_lut, static_cast<size_t>(g) * g * 256));
+            // with a previous frame at hand the temporal blend rides on CLAHE's apply pass: the un-blended frame goes to
+            // hr[cur ^ 1] (it becomes up_{t-1}), the blended one straight to d_out
+            TemporalFuse tf{static_cast<const uint8_t*>(h->prev_up.p), d_out, alpha, tau};
+            const bool want_fuse = o.temporal && prev_ok && out_stride == hr_stride;
             VR_TRY(launch_clahe(dev, cur_ptr(), hr_stride, sH, sW, dst, dstride, o.clahe_clip > 0 ? o.clahe_clip : 2.0f, g,
-                                static_cast<int32_t*>(h->clahe_hist.p), static_cast<uint8_t*>(h->clahe_lut.p), nullptr));
+                                static_cast<int32_t*>(h->clahe_hist.p), static_cast<uint8_t*>(h->clahe_lut.p), nullptr,
+                                want_fuse ? &tf : nullptr, &temporal_done));
             if (!last) cur ^= 1;
         }
-        if (o.temporal) {
-            const float alpha = o.temporal_alpha > 0 ? o.temporal_alpha : 0.2f;
-            const float tau = o.temporal_tau > 0 ? o.temporal_tau : 12.f;
-            if (h->has_prev && h->prev_h == sH && h->prev_w == sW) {
+        if (o.temporal && temporal_done) {
+            std::swap(h->hr[cur], h->prev_up);  // up_t becomes up_{t-1}; no copy
+        } else if (o.temporal) {
+            if (prev_ok) {
                 VR_TRY(launch_temporal(dev, cur_ptr(), hr_stride, static_cast<const uint8_t*>(h->prev_up.p), hr_stride,
                                        sH, sW, d_out, out_stride, alpha, tau));
             } else {

@@ -41,13 +41,14 @@ struct Pair2 {
 // The static box sequence of one work item: step s = A's row pair s (chunks 0..nchA-1), then B's row pair s - kLag (chunks
 // 0..nchA-1 from TMA, chunk nchA from the hand-off slot).
 struct Pair2Iter {
-    int nA2, nB2, nchA, S;
+    int nA2, nB2, nchA, S, lag;
     int s, part, c;
-    __device__ __forceinline__ void init(int nin2B, int nch_a) {
+    __device__ __forceinline__ void init(int nin2B, int nch_a, int lag_) {
         nB2 = nin2B >> 1;
         nA2 = nB2 + 1;
         nchA = nch_a;
-        S = nB2 + Pair2::kLag;
+        lag = lag_;
+        S = nB2 + lag;
         s = 0;
         part = 0;
         c = 0;
@@ -61,7 +62,7 @@ struct Pair2Iter {
                 part = 1;
                 c = 0;
             }
-            const int b = s - Pair2::kLag;
+            const int b = s - lag;
             if (b >= 0 && b < nB2) return;
             part = 0;
             c = 0;
@@ -80,7 +81,7 @@ struct Pair2Iter {
             normalize();
         }
     }
-    __device__ __forceinline__ int pair_index() const { return part == 0 ? s : s - Pair2::kLag; }
+    __device__ __forceinline__ int pair_index() const { return part == 0 ? s : s - lag; }
     __device__ __forceinline__ bool hand() const { return part == 1 && c == nchA; }
     __device__ __forceinline__ bool last_chunk() const { return c == (part == 0 ? nchA - 1 : nchA); }
     __device__ __forceinline__ int boxes() const { return nA2 * nchA + nB2 * (nchA + 1); }
@@ -119,6 +120,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     uint64_t* wfull = hempty + Pair2::kHand;
     const int nslots = a.nstages;
     const int nchA = a.nchunks, nchB = a.nchunks + 1;
+    const int lag = a.lag < 1 ? Pair2::kLag : a.lag;  // B runs `lag` row pairs behind A (>= 2: the hand-off needs A's pair b + 1 drained)
     uint8_t* wB = smem + nchA * T::kBHalf;
     uint8_t* hand0 = wB + nchB * T::kBHalf;
     uint8_t* slot0 = hand0 + Pair2::kHand * T::kASlot;
@@ -127,6 +129,9 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const long long t_start = clock64();
+    // VR profiling hook (dbg_cycles set by the test hook only): cluster 0's leader CTA accumulates the cycles its warps spend
+    // in each kind of wait into dbg_cycles[300..340)
+    const bool prof = a.dbg_cycles != nullptr && blockIdx.x == 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPairMaxSlots; ++i) {
@@ -202,16 +207,19 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
             const uint32_t lead_full = ptx::map_to_rank(&full[0], 0);
             int s = 0;
             uint32_t ph = 0;
+            long long pc[1] = {0};
             for (int item = cluster_id; item < num_items; item += nclusters) {
                 const PairSub me = pair2_sub(a, 2 * item + static_cast<int>(rank));
                 const int xc = me.sx * Pair2::kStrip - 2;  // box column 0: one pixel left of the strip's first (halo) pixel
                 Pair2Iter it;
-                it.init((pair_rows(a, item) + 3) & ~1, nchA);
+                it.init((pair_rows(a, item) + 3) & ~1, nchA, lag);
                 for (; !it.done(); it.next()) {
                     if (it.hand()) continue;
                     // A's input rows start one row above B's: A computes the band plus a halo row on either side
-                    const int yrow = it.part == 0 ? me.y0 - 2 + 2 * it.s : me.y0 - 1 + 2 * (it.s - Pair2::kLag);
+                    const int yrow = it.part == 0 ? me.y0 - 2 + 2 * it.s : me.y0 - 1 + 2 * (it.s - lag);
+                    const long long tw0 = prof ? clock64() : 0;
                     ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (prof) pc[0] += clock64() - tw0;
                     if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
                     const int ch0 = a.cin_off + it.c * T::KC;
                     ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0, xc, yrow,
@@ -219,21 +227,27 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                     if (++s == nslots) { s = 0; ph ^= 1; }
                 }
             }
+            if (prof) {
+                a.dbg_cycles[300] = pc[0];                 // producer: cycles waiting for a free TMA slot
+                a.dbg_cycles[301] = clock64() - t_start;
+            }
         }
     } else if (warp > T::kEpi) {
         // ===================== MMA issuers: leader only; two warps alternate units of boxes as in K3 =====================
         if (rank == 0) {
             const int mw = warp - (T::kEpi + 1);
             const int unit = a.unit < 1 ? 1 : a.unit;
+            const bool skip_mma = (a.flags & FLAG_SKIP_MMA) != 0;
             int s = 0;           // TMA slot ring
             uint32_t ph = 0;
             uint32_t hcnt = 0;   // hand-off boxes consumed so far (slot = hcnt % kHand)
             int gunit = 0;
             uint32_t g0A = 0, g0B = 0;  // logical rows started before the current item, per layer
+            long long ic[5] = {0, 0, 0, 0, 0};  // full, tempty, hfull, hand-over (bar.sync), issue pass
             for (int item = cluster_id; item < num_items; item += nclusters) {
                 const int nin2B = (pair_rows(a, item) + 3) & ~1, nin2A = nin2B + 2;
                 Pair2Iter it;
-                it.init(nin2B, nchA);
+                it.init(nin2B, nchA, lag);
                 const int nb = it.boxes();
                 for (int n = 0; n < nb; n += unit, ++gunit) {
                     const int cnt = nb - n < unit ? nb - n : unit;
@@ -243,13 +257,17 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                         int ss = s;
                         uint32_t pp = ph, hh = hcnt;
                         for (int i = 0; i < cnt; ++i, w.next()) {
+                            long long t0 = prof ? clock64() : 0;
                             if (w.hand()) {
                                 ptx::mbar_wait(&hfull[hh % Pair2::kHand], (hh / Pair2::kHand) & 1u);
                                 ++hh;
+                                if (prof) ic[2] += clock64() - t0;
                             } else {
                                 ptx::mbar_wait(&full[ss], pp);
                                 if (++ss == nslots) { ss = 0; pp ^= 1; }
+                                if (prof) ic[0] += clock64() - t0;
                             }
+                            t0 = prof ? clock64() : 0;
                             if (w.c == 0) {
                                 // logical rows first touched by this row pair: ga + 2, ga + 3 (and ga, ga + 1 at the top of an item)
                                 const int jj = 2 * w.pair_index();
@@ -257,11 +275,15 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                                 uint64_t* te = tempty + w.part * P;
                                 for (uint32_t gl = (jj == 0 ? ga : ga + 2); gl < ga + 4; ++gl)
                                     ptx::mbar_wait(&te[gl % P], ((gl / P) & 1u) ^ 1u);
+                                if (prof) ic[1] += clock64() - t0;
                             }
                         }
                         ptx::tc_fence_after();
+                        const long long t1 = prof ? clock64() : 0;
                         if (gunit > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+                        if (prof) ic[3] += clock64() - t1;
                     }
+                    const long long t2 = prof ? clock64() : 0;
                     if (ptx::elect_one()) {
                         Pair2Iter w = it;
                         int ss = s;
@@ -276,7 +298,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                             if (mine) {
                                 const uint8_t* aslot = hand ? hand0 + (hh % Pair2::kHand) * T::kASlot : slot0 + ss * T::kASlot;
                                 const uint8_t* bw = (L == 0 ? smem : wB) + w.c * T::kBHalf;
-                                pair_issue_box<N>(tb + s0 * N, tb + s1 * N, ptx::smem_u32(aslot) >> 4, ptx::smem_u32(bw) >> 4);
+                                if (!skip_mma) pair_issue_box<N>(tb + s0 * N, tb + s1 * N, ptx::smem_u32(aslot) >> 4, ptx::smem_u32(bw) >> 4);
                                 ptx::umma_commit_pair(hand ? &hempty[hh % Pair2::kHand] : &empty[ss]);
                             }
                             if (w.last_chunk()) {
@@ -293,6 +315,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                         }
                     }
                     __syncwarp();
+                    if (prof && mine) ic[4] += clock64() - t2;
                     if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");
                     for (int i = 0; i < cnt; ++i, it.next()) {
                         if (it.hand()) ++hcnt;
@@ -304,6 +327,11 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
             }
             // the last unit's arrive has no matching sync: consume it so no named barrier is left half-arrived
             if (gunit > 0 && (gunit & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+            if (prof && lane == 0) {
+                for (int i = 0; i < 5; ++i) a.dbg_cycles[310 + mw * 8 + i] = ic[i];
+                a.dbg_cycles[310 + mw * 8 + 5] = clock64() - t_start;
+                a.dbg_cycles[310 + mw * 8 + 6] = gunit;
+            }
         }
     } else {
         // ===================== epilogue warps (both CTAs): warp % 4 = TMEM lane quarter, warp / 4 = row group =====================
@@ -317,6 +345,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
         const bool owned_col = local >= 1 && local <= Pair2::kStrip;
         const float slope = a.slope;
         uint32_t g0A = 0, g0B = 0, hbase = 0;  // hbase: hand-off row pairs filled before the current item
+        long long ec[3] = {0, 0, 0};  // tfull waits, hempty waits, rows
         for (int item = cluster_id; item < num_items; item += nclusters) {
             const PairSub me = pair2_sub(a, 2 * item + static_cast<int>(rank));
             const int y0 = me.y0, nrow = me.nrow;
@@ -326,12 +355,14 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
             bool xgap = false;
             for (int j = 0; j < a.ngx; ++j) xgap |= (x_in && (x >> a.gshift) == a.gx[j]);
             const int nA2 = nin2A >> 1, nB2 = nin2B >> 1;
-            const int S = nB2 + Pair2::kLag;
+            const int S = nB2 + lag;
             // one logical row of layer L: drain, hand the ring position back, then (real rows) activation -> fp16 -> hand-off / global
             auto do_row = [&](int L, int l) {
                 const uint32_t gl = (L == 0 ? g0A : g0B) + l;
                 const uint32_t m = gl % P;
+                const long long te0 = prof ? clock64() : 0;
                 ptx::mbar_wait(&tfull[L * P + m], (gl / P) & 1u);
+                if (prof) { ec[0] += clock64() - te0; ec[2] += 1; }
                 ptx::tc_fence_after();
                 const uint32_t t_main = tmem_base + lane_base + L * Pair2::kRingCols + m * N;
                 const uint32_t t_mir = m < 2 ? tmem_base + lane_base + L * Pair2::kRingCols + (P + m) * N : 0xffffffffu;
@@ -360,10 +391,18 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = zero ? 0.f : fmaxf(v[j], v[j] * slope);
                 const uint4 h0 = pack8(v), h1 = pack8(v + 8), h2 = pack8(v + 16), h3 = pack8(v + 24);
-                if (handoff) {
+                if (handoff && (a.flags & FLAG_SKIP_EPI)) {  // ablation: hand-off protocol without the data
                     const uint32_t f = hbase + static_cast<uint32_t>(jB >> 1);
                     const uint32_t q = f % Pair2::kHand;
                     ptx::mbar_wait(&hempty[q], ((f / Pair2::kHand) & 1u) ^ 1u);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(lead_hfull + q * 8);
+                } else if (handoff) {
+                    const uint32_t f = hbase + static_cast<uint32_t>(jB >> 1);
+                    const uint32_t q = f % Pair2::kHand;
+                    const long long th0 = prof ? clock64() : 0;
+                    ptx::mbar_wait(&hempty[q], ((f / Pair2::kHand) & 1u) ^ 1u);
+                    if (prof) ec[1] += clock64() - th0;
                     hand_store(hand_s + q * T::kASlot, jB & 1, 1 + local, h0, h1, h2, h3);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -383,7 +422,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                     do_row(0, 2 * s + static_cast<int>(rgrp));
                     if (s == nA2 - 1) do_row(0, nin2A + static_cast<int>(rgrp));
                 }
-                const int b = s - Pair2::kLag;
+                const int b = s - lag;
                 if (b >= 0 && b < nB2) {
                     do_row(1, 2 * b + static_cast<int>(rgrp));
                     if (b == nB2 - 1) do_row(1, nin2B + static_cast<int>(rgrp));
@@ -392,6 +431,10 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
             g0A += nin2A + 2;
             g0B += nin2B + 2;
             hbase += static_cast<uint32_t>(nB2);
+        }
+        if (prof && lane == 0 && (warp == 0 || warp == 4)) {
+            for (int i = 0; i < 3; ++i) a.dbg_cycles[330 + (warp >> 2) * 4 + i] = ec[i];
+            a.dbg_cycles[330 + (warp >> 2) * 4 + 3] = clock64() - t_start;
         }
     }
 

@@ -386,6 +386,7 @@ static int launch_pair2(Device& dev, const CUtensorMap& tm, ConvArgs a, const Co
     a.bias2 = wb.bias;
     a.nstages = nslots;
     a.unit = dev.pair_unit > 0 && dev.pair_unit <= 3 ? dev.pair_unit : 2;
+    a.lag = dev.k4_lag >= 2 && dev.k4_lag <= 4 ? dev.k4_lag : 0;
     if (a.unit > nslots) a.unit = nslots;
     a.tiles_x = (a.W + Pair2::kStrip - 1) / Pair2::kStrip;
     const int max_clusters = dev.sm_count / 2;
@@ -429,6 +430,7 @@ void read_conv_env(Device& dev) {
     geti("VR_MAX_CTAS", &dev.max_ctas);
     geti("VR_EPI_DIRECT", &dev.epi_direct);
     geti("VR_K4", &dev.fuse_pairs);
+    geti("VR_K4_LAG", &dev.k4_lag);
     geti("VR_EARLY64", &dev.early64);
     geti("VR_UNIT", &dev.pair_unit);
     geti("VR_L2HINT", &dev.l2_hint);

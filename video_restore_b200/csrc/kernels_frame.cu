@@ -31,7 +31,7 @@ bool clahe_vec_ok(const uint8_t* src, int64_t sstride, int H, int W, const uint8
 int launch_clahe_hist_vec(Device& dev, const uint8_t* src, int64_t sstride, int tile_w, int tile_h, int tiles_x,
                           int ntiles, int32_t* d_hist);
 int launch_clahe_apply_vec(Device& dev, const uint8_t* src, uint8_t* dst, int H, int W, const uint8_t* d_lut,
-                           int tiles_x, int tiles_y, float inv_tw, float inv_th);
+                           int tiles_x, int tiles_y, float inv_tw, float inv_th, const TemporalFuse* tf);
 
 #define VR_LAUNCH_CHECK(dev)                                   \
     do {                                                       \
@@ -548,7 +548,9 @@ clahe_apply_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int 
     o[2] = static_cast<uint8_t>(min(max(nr, 0), 255));
 }
 int launch_clahe(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
-                 float clip_limit, int grid_n, int32_t* d_hist, uint8_t* d_lut, uint8_t* /*d_luma*/) {
+                 float clip_limit, int grid_n, int32_t* d_hist, uint8_t* d_lut, uint8_t* /*d_luma*/, const TemporalFuse* tf,
+                 bool* fused) {
+    if (fused) *fused = false;
     if (grid_n < 1 || grid_n > 16) {
         set_error(dev.err, "clahe: grid must be 1..16");
         return -1;
@@ -585,7 +587,12 @@ int launch_clahe(Device& dev, const uint8_t* src, int64_t sstride, int H, int W,
     clahe_lut_kernel<<<ntiles, 256, 0, dev.stream>>>(d_hist, d_lut, clip, lut_scale);
     VR_LAUNCH_CHECK(dev);
     const float inv_tw = 1.0f / static_cast<float>(tile_w), inv_th = 1.0f / static_cast<float>(tile_h);
-    if (vec) return launch_clahe_apply_vec(dev, src, dst, H, W, d_lut, tiles_x, tiles_y, inv_tw, inv_th);
+    if (vec) {
+        const bool fuse = tf && tf->prev && tf->blended && (reinterpret_cast<uintptr_t>(tf->prev) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(tf->blended) & 15) == 0;
+        if (fused) *fused = fuse;
+        return launch_clahe_apply_vec(dev, src, dst, H, W, d_lut, tiles_x, tiles_y, inv_tw, inv_th, fuse ? tf : nullptr);
+    }
     clahe_apply_kernel<<<dim3((W + 255) / 256, H), 256, 0, dev.stream>>>(src, sstride, H, W, dst, dstride, d_lut,
                                                                          tiles_x, tiles_y, inv_tw, inv_th);
     VR_LAUNCH_CHECK(dev);

@@ -115,9 +115,13 @@ clahe_hist_vec_kernel(const uint8_t* __restrict__ src, int64_t sstride, int tile
     if (s) atomicAdd(&hist[tile * 256 + threadIdx.x], static_cast<int>(s));
 }
 
+// kTemporal: the temporal stage fused in -- the un-blended result (next frame's "previous") goes to dst, the frame blended with
+// `prev` to `blended`: one pass instead of two (reads src + prev, writes dst + blended; the separate temporal kernel re-read dst).
+template <bool kTemporal>
 __global__ void __launch_bounds__(256)
 clahe_apply_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
-                       const uint8_t* __restrict__ lut, int tiles_x, int tiles_y, float inv_tw, float inv_th) {
+                       const uint8_t* __restrict__ lut, int tiles_x, int tiles_y, float inv_tw, float inv_th,
+                       const uint8_t* __restrict__ prev, uint8_t* __restrict__ blended, float alpha, float one_minus, float tau) {
     const int cpr = W / 16;
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i >= static_cast<size_t>(cpr) * H) return;
@@ -158,6 +162,26 @@ clahe_apply_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ ds
         o.b[3 * k + 2] = sat_u8(Yn + ((crd * 22987 + 8192) >> 14));
     }
     store_px16(dst + i * 48, o);
+    if constexpr (kTemporal) {
+        Px16 p, t;
+        load_px16(prev + i * 48, p);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {  // temporal_vec_kernel's arithmetic, on the registers just produced
+            const int c0 = o.b[3 * k], c1 = o.b[3 * k + 1], c2 = o.b[3 * k + 2];
+            const int p0 = p.b[3 * k], p1 = p.b[3 * k + 1], p2 = p.b[3 * k + 2];
+            const int d = max(max(abs(c0 - p0), abs(c1 - p1)), abs(c2 - p2));
+            if (static_cast<float>(d) < tau) {
+                t.b[3 * k] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c0)), __fmul_rn(alpha, static_cast<float>(p0)))));
+                t.b[3 * k + 1] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c1)), __fmul_rn(alpha, static_cast<float>(p1)))));
+                t.b[3 * k + 2] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c2)), __fmul_rn(alpha, static_cast<float>(p2)))));
+            } else {
+                t.b[3 * k] = o.b[3 * k];
+                t.b[3 * k + 1] = o.b[3 * k + 1];
+                t.b[3 * k + 2] = o.b[3 * k + 2];
+            }
+        }
+        store_px16(blended + i * 48, t);
+    }
 }
 
 bool clahe_vec_ok(const uint8_t* src, int64_t sstride, int H, int W, const uint8_t* dst, int64_t dstride, int grid_n) {
@@ -177,11 +201,15 @@ int launch_clahe_hist_vec(Device& dev, const uint8_t* src, int64_t sstride, int 
     return 0;
 }
 int launch_clahe_apply_vec(Device& dev, const uint8_t* src, uint8_t* dst, int H, int W, const uint8_t* d_lut,
-                           int tiles_x, int tiles_y, float inv_tw, float inv_th) {
+                           int tiles_x, int tiles_y, float inv_tw, float inv_th, const TemporalFuse* tf) {
     const size_t n = static_cast<size_t>(W / 16) * H;
-    clahe_apply_vec_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, dev.stream>>>(src, dst, H, W, d_lut,
-                                                                                           tiles_x, tiles_y, inv_tw,
-                                                                                           inv_th);
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (tf)
+        clahe_apply_vec_kernel<true><<<grid, 256, 0, dev.stream>>>(src, dst, H, W, d_lut, tiles_x, tiles_y, inv_tw, inv_th, tf->prev,
+                                                                   tf->blended, tf->alpha, 1.0f - tf->alpha, tf->tau);
+    else
+        clahe_apply_vec_kernel<false><<<grid, 256, 0, dev.stream>>>(src, dst, H, W, d_lut, tiles_x, tiles_y, inv_tw, inv_th, nullptr,
+                                                                    nullptr, 0.f, 0.f, 0.f);
     VR_LAUNCH_CHECK(dev);
     return 0;
 }

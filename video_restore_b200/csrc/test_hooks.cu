@@ -192,12 +192,18 @@ extern "C" int vr_conv3x3_test(vr_conv_test* t) {
     return rc;
 }
 
+static long long g_pair2_prof[64] = {0};
+// wait-cycle profile of cluster 0's leader CTA in the last vr_conv_pair2_test launch (dbg_cycles[300..364), see the kernel)
+extern "C" void vr_pair2_profile(int64_t* out64) {
+    for (int i = 0; i < 64; ++i) out64[i] = g_pair2_prof[i];
+}
+
 // K4 hook: two consecutive dense-block layers in one launch. x [H][W][cin] (cin % 32 == 0), layer A cin -> 32, layer B
 // (cin + 32) -> 32, both + bias + LeakyReLU(slope); yA / yB [H][W][32]. Tensors are the network's chunk-planar dense-block
 // buffer (cin / 32 + 2 planes). iters > 1: average ms per launch in *ms. flags: VR_MAX_CTAS etc. through the environment.
 extern "C" int vr_conv_pair2_test(int32_t device, int32_t H, int32_t W, int32_t cin, const float* x, const float* wa, const float* ba,
                                   const float* wb, const float* bb, float slope, float* ya, float* yb, int32_t iters, float* ms,
-                                  const int32_t* gaps_x, int32_t ngx, const int32_t* gaps_y, int32_t ngy) {
+                                  const int32_t* gaps_x, int32_t ngx, const int32_t* gaps_y, int32_t ngy, int32_t flags) {
     if (!x || !wa || !wb || !ya || !yb || H <= 0 || W <= 0 || cin <= 0 || cin % 32 != 0 || ngx > 7 || ngy > 7) {
         set_error(nullptr, "vr_conv_pair2_test: bad arguments");
         return VR_E_INVALID;
@@ -239,6 +245,11 @@ extern "C" int vr_conv_pair2_test(int32_t device, int32_t H, int32_t W, int32_t 
     c.out_pstride = static_cast<long long>(px) * 32;
     c.out_coff = cin;
     c.out_coff2 = cin + 32;
+    c.flags = flags;
+    long long* d_cyc = nullptr;
+    cudaMalloc(&d_cyc, 1024 * sizeof(long long));
+    cudaMemset(d_cyc, 0, 1024 * sizeof(long long));
+    c.dbg_cycles = d_cyc;
     c.ngx = ngx;
     c.ngy = ngy;
     for (int i = 0; i < ngx; ++i) c.gx[i] = gaps_x[i];
@@ -290,6 +301,12 @@ extern "C" int vr_conv_pair2_test(int32_t device, int32_t H, int32_t W, int32_t 
             set_error(dev.err, "pair2 kernel modified its source planes");
             rc = VR_E_CUDA;
         }
+    }
+    if (d_cyc) {
+        long long tmp[1024];
+        if (cudaMemcpy(tmp, d_cyc, sizeof(tmp), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int i = 0; i < 64; ++i) g_pair2_prof[i] = tmp[300 + i];
+        cudaFree(d_cyc);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

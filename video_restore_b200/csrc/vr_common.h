@@ -118,6 +118,7 @@ struct Device {
     // VR_EARLY64 = 0 / 1 / 2 when a 64-channel row's ring position goes back (ConvArgs::early64); VR_UNIT boxes per issuer
     // hand-over (0 = automatic); VR_L2HINT / VR_L2FRAC cache-policy experiments (ConvArgs::l2_hint)
     int epi_direct = 1;
+    int k4_lag = 0;       // VR_K4_LAG: K4's row-pair lag of layer B (0 = default)
     int fuse_pairs = 1;   // VR_K4=0: conv1+conv2 / conv3+conv4 of a dense block as separate K3 launches (A/B runs)
     int early64 = 2;
     int pair_unit = 0;
@@ -168,8 +169,16 @@ int launch_bilateral(Device& dev, const uint8_t* src, int64_t sstride, int H, in
                      int d, float sigma_color, float sigma_space);
 int launch_unsharp(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
                    float amount);
+// temporal stage fused into CLAHE's apply pass (vectorised path only): dst receives the UN-blended frame (the next frame's
+// "previous"), `blended` (dense rows) the frame blended with `prev`. *fused tells the caller whether it happened.
+struct TemporalFuse {
+    const uint8_t* prev;
+    uint8_t* blended;
+    float alpha, tau;
+};
 int launch_clahe(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
-                 float clip, int grid, int32_t* d_hist, uint8_t* d_lut, uint8_t* d_luma);
+                 float clip, int grid, int32_t* d_hist, uint8_t* d_lut, uint8_t* d_luma, const TemporalFuse* tf = nullptr,
+                 bool* fused = nullptr);
 int launch_temporal(Device& dev, const uint8_t* cur, int64_t cstride, const uint8_t* prev, int64_t pstride, int H,
                     int W, uint8_t* dst, int64_t dstride, float alpha, float tau);
 int launch_blend_weights(Device& dev, int extent, float* d_w);
