@@ -176,9 +176,10 @@ def pair2_profile():
     a = np.zeros(64, np.int64)
     load().vr_pair2_profile(a.ctypes.data_as(C.c_void_p))
     names = {0: "producer.wait_empty", 1: "producer.total"}
-    for mw in (0, 1):
-        for i, n in enumerate(("wait_full", "wait_tempty", "wait_hfull", "handover", "issue", "total", "units")):
-            names[10 + mw * 8 + i] = f"issuer{mw}.{n}"
+    for i, n in enumerate(("wait_for_waiter", "issue", "-", "loop_total", "units", "prologue")):
+        names[10 + i] = f"issuer.{n}"
+    for i, n in enumerate(("wait_for_issuer", "barrier_waits", "walk", "loop_total", "units", "prologue")):
+        names[18 + i] = f"waiter.{n}"
     for g in (0, 1):
         for i, n in enumerate(("wait_tfull", "wait_hempty", "rows", "total")):
             names[30 + g * 4 + i] = f"epilogue{g}.{n}"

@@ -40,20 +40,23 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build(verbose: bool = False, force: bool = False) -> Path:
+def build(verbose: bool = False, force: bool = False, extra_flags=(), lib: Path = LIB, obj_dir: Path = OBJ) -> Path:
+    """extra_flags / lib / obj_dir: an instrumented second library next to the product one, e.g.
+    `python -m video_restore_b200.build --prof` -> libvrb200_prof.so with -DVR_K4_PROF (select it with VR_LIB=...)."""
     nvcc = _nvcc()
-    OBJ.mkdir(parents=True, exist_ok=True)
+    OBJ_ = obj_dir
+    OBJ_.mkdir(parents=True, exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "vrb200.h"]
     jobs = []
     for src in sources:
-        obj = OBJ / (src.stem + ".o")
+        obj = OBJ_ / (src.stem + ".o")
         if force or _stale(obj, [src, *headers]):
             jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -66,16 +69,20 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
-    objs = [OBJ / (s.stem + ".o") for s in sources]
-    if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
+    objs = [OBJ_ / (s.stem + ".o") for s in sources]
+    if force or jobs or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-o", str(lib), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
                "-Xcompiler", "-fPIC", "-Xlinker", "--no-undefined"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    p = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
+    if "--prof" in sys.argv:
+        p = build(verbose="-v" in sys.argv, force="-f" in sys.argv, extra_flags=("-DVR_K4_PROF",),
+                  lib=PKG / "libvrb200_prof.so", obj_dir=PKG / "csrc" / "_obj_prof")
+    else:
+        p = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
     print(p)

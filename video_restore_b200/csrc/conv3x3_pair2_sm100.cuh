@@ -33,7 +33,8 @@ struct Pair2 {
     static constexpr int kHand = 2;          // hand-off slots (row pairs of x_k in flight between A's epilogue and B's MMAs)
     static constexpr int kLag = 2;           // B runs this many row pairs behind A
     static constexpr int kStrip = 126;       // output pixels per strip
-    static constexpr int kThreads = T::kThreads;
+    static constexpr int kEpi = 16;          // epilogue warps: four groups = (layer A | B) x (even | odd logical row)
+    static constexpr int kThreads = (kEpi + 1 + kMmaWarps) * 32;
     static constexpr int kBudget = 227 * 1024 - 1024 - 4096;   // dynamic shared memory: weights + hand-off + TMA slots
     static constexpr int kMinSlots = 4;
 };
@@ -131,7 +132,11 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     const long long t_start = clock64();
     // VR profiling hook (dbg_cycles set by the test hook only): cluster 0's leader CTA accumulates the cycles its warps spend
     // in each kind of wait into dbg_cycles[300..340)
+#ifdef VR_K4_PROF
     const bool prof = a.dbg_cycles != nullptr && blockIdx.x == 0;
+#else
+    constexpr bool prof = false;   // build with -DVR_K4_PROF for the wait-cycle counters (tools/k4_profile.py)
+#endif
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPairMaxSlots; ++i) {
@@ -139,7 +144,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
             ptx::mbar_init(&empty[i], 1);
         }
         for (uint32_t i = 0; i < 2 * P; ++i) {
-            ptx::mbar_init(&tfull[i], kMmaWarps);   // both issuer warps commit (multicast) their MMAs of the row
+            ptx::mbar_init(&tfull[i], 1);           // the one issuing thread commits (multicast) the row's MMAs
             ptx::mbar_init(&tempty[i], 8);          // four lane-quarter warps in each of the two CTAs
         }
         for (int i = 0; i < Pair2::kHand; ++i) {
@@ -149,7 +154,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
         ptx::mbar_init(wfull, 1);
         ptx::fence_mbar_init();
     }
-    if (warp == T::kEpi) {
+    if (warp == Pair2::kEpi) {
         if (lane == 0) ptx::prefetch_tmap(&tmap);
         __syncwarp();
         ptx::tmem_alloc_pair<512>(&s_tmem_slot);
@@ -167,7 +172,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_slot;
-    if (warp == T::kEpi && lane == 0) {
+    if (warp == Pair2::kEpi && lane == 0) {
         // this CTA's halves of both layers' weight rows; weights are never written by a kernel: fetch before the dependency wait
         const __half* wpa = a.wpack + (static_cast<size_t>(rank) * nchA) * (T::kBHalf / 2);
         const __half* wpb = a.wpack2 + (static_cast<size_t>(rank) * nchB) * (T::kBHalf / 2);
@@ -175,19 +180,17 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
         for (int c = 0; c < nchA; ++c) ptx::bulk_load(smem + c * T::kBHalf, wpa + static_cast<size_t>(c) * (T::kBHalf / 2), T::kBHalf, wfull);
         for (int c = 0; c < nchB; ++c) ptx::bulk_load(wB + c * T::kBHalf, wpb + static_cast<size_t>(c) * (T::kBHalf / 2), T::kBHalf, wfull);
     }
-    if (warp < T::kEpi) {
+    if (warp < Pair2::kEpi) {
         // ring blocks start as the bias row of their layer, mirror blocks as zero; every MMA accumulates
         const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const int L = warp >> 3;   // warps 0..7 initialise layer A's ring, 8..15 layer B's
+        float bz[32];
 #pragma unroll
-        for (int L = 0; L < 2; ++L) {
-            float bz[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bz[j] = s_bias[L][j];
-            for (uint32_t blk = warp >> 2; blk < static_cast<uint32_t>(Pair2::kPhys); blk += T::kGroups) {
-                const uint32_t t = tmem_base + lane_base + L * Pair2::kRingCols + blk * N;
-                if (blk < P) ptx::tmem_st32(t, bz);
-                else ptx::tmem_st32_zero(t);
-            }
+        for (int j = 0; j < 32; ++j) bz[j] = s_bias[L][j];
+        for (uint32_t blk = (warp >> 2) & 1; blk < static_cast<uint32_t>(Pair2::kPhys); blk += 2) {
+            const uint32_t t = tmem_base + lane_base + L * Pair2::kRingCols + blk * N;
+            if (blk < P) ptx::tmem_st32(t, bz);
+            else ptx::tmem_st32_zero(t);
         }
         ptx::tmem_st_wait();
     }
@@ -201,7 +204,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     const int num_items = (a.tiles_x * a.nbands + 1) >> 1;
     const int cluster_id = static_cast<int>(blockIdx.x) >> 1, nclusters = static_cast<int>(gridDim.x) >> 1;
 
-    if (warp == T::kEpi) {
+    if (warp == Pair2::kEpi) {
         // ===================== TMA producer: this CTA's strip; bytes counted on the leader's barrier =====================
         if (lane == 0) {
             const uint32_t lead_full = ptx::map_to_rank(&full[0], 0);
@@ -220,10 +223,14 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                     const long long tw0 = prof ? clock64() : 0;
                     ptx::mbar_wait(&empty[s], ph ^ 1);
                     if (prof) pc[0] += clock64() - tw0;
-                    if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
-                    const int ch0 = a.cin_off + it.c * T::KC;
-                    ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0, xc, yrow,
-                                          a.in_cstride == 32 ? ch0 >> 5 : 0);
+                    if (a.flags & FLAG_SKIP_TMA) {  // ablation: the slot protocol without the loads
+                        if (rank == 0) ptx::mbar_arrive(&full[s]);
+                    } else {
+                        if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
+                        const int ch0 = a.cin_off + it.c * T::KC;
+                        ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0, xc, yrow,
+                                              a.in_cstride == 32 ? ch0 >> 5 : 0);
+                    }
                     if (++s == nslots) { s = 0; ph ^= 1; }
                 }
             }
@@ -232,111 +239,164 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                 a.dbg_cycles[301] = clock64() - t_start;
             }
         }
-    } else if (warp > T::kEpi) {
-        // ===================== MMA issuers: leader only; two warps alternate units of boxes as in K3 =====================
+    } else if (warp > Pair2::kEpi) {
+        // ===================== MMA issue: leader only; one ISSUER warp and one WAITER warp =====================
+        // K3 alternates two issuing warps, each waiting for its own unit's barriers while the other issues. Measured on K4 with
+        // the wait-cycle counters: that overlap does not happen -- rows receive MMAs from both warps, so both must tcgen05.commit
+        // every accumulator-ready barrier, and a commit queues behind the other warp's MMAs in the (shallow) tensor-pipe FIFO:
+        // the non-owner cannot run ahead to its next wait pass, and every unit pays wait pass + issue in sequence (the bare
+        // barrier skeleton, no MMAs / TMA / TMEM traffic, ran at 59 of the kernel's 88 us). Here ONE elected thread issues every
+        // MMA and every commit (accumulator-ready barriers need one arrival) and never touches an mbarrier; the waiter warp does
+        // all the waiting one unit ahead and hands units over through two alternating pairs of named barriers.
+        // Both warps walk the box sequence ONCE, with incremental state only (slot / hand-off / ring positions advance by adds
+        // and wraps: no divisions, no iterator object): with ~500 cycles of tensor work per box, every ~100 scalar instructions
+        // per box in either warp cost as much as the MMAs themselves. Units of `a.unit` boxes (3) are handed over; a unit per
+        // (layer, row pair) with a closed-form barrier list was measured too: same on conv1+2, 10 % slower on conv3+4, whose six
+        // TMA slots cannot hold the next 4-box unit while the current one is being issued.
         if (rank == 0) {
-            const int mw = warp - (T::kEpi + 1);
+            const bool issuer = warp == Pair2::kEpi + 1;
             const int unit = a.unit < 1 ? 1 : a.unit;
             const bool skip_mma = (a.flags & FLAG_SKIP_MMA) != 0;
-            int s = 0;           // TMA slot ring
-            uint32_t ph = 0;
-            uint32_t hcnt = 0;   // hand-off boxes consumed so far (slot = hcnt % kHand)
-            int gunit = 0;
-            uint32_t g0A = 0, g0B = 0;  // logical rows started before the current item, per layer
-            long long ic[5] = {0, 0, 0, 0, 0};  // full, tempty, hfull, hand-over (bar.sync), issue pass
+            const uint32_t slot0_lo = ptx::smem_u32(slot0) >> 4, hand0_lo = ptx::smem_u32(hand0) >> 4;
+            const uint32_t wA_lo = ptx::smem_u32(smem) >> 4, wB_lo = ptx::smem_u32(wB) >> 4;
+            constexpr uint32_t kSlotLo = T::kASlot >> 4, kBHalfLo = T::kBHalf >> 4;
+            const uint32_t full_s = ptx::smem_u32(full), hfull_s = ptx::smem_u32(hfull), tempty_s = ptx::smem_u32(tempty);
+            int ss = 0;              // TMA slot ring: index and phase
+            uint32_t sph = 0;
+            uint32_t hq = 0, hph = 0;  // hand-off slot ring: index and phase
+            int gunit = 0, par = 0, ubox = 0;
+            uint32_t pos[2] = {0, 0}, rev[2] = {0, 0};  // per layer: ring position / revolution count of the current pair's first row
+            int k = 0;                 // waiter: barrier list entries of the current unit
+            uint32_t my_bar = 0u, my_par = 0u;  // shared-memory address of this lane's barrier (0 = none)
+            long long ic[4] = {0, 0, 0, 0};
+            const long long t_loop = prof ? clock64() : 0;
+            long long tp0 = t_loop;
             for (int item = cluster_id; item < num_items; item += nclusters) {
-                const int nin2B = (pair_rows(a, item) + 3) & ~1, nin2A = nin2B + 2;
-                Pair2Iter it;
-                it.init(nin2B, nchA, lag);
-                const int nb = it.boxes();
-                for (int n = 0; n < nb; n += unit, ++gunit) {
-                    const int cnt = nb - n < unit ? nb - n : unit;
-                    const bool mine = (gunit & 1) == mw;
-                    if (mine) {
-                        Pair2Iter w = it;
-                        int ss = s;
-                        uint32_t pp = ph, hh = hcnt;
-                        for (int i = 0; i < cnt; ++i, w.next()) {
-                            long long t0 = prof ? clock64() : 0;
-                            if (w.hand()) {
-                                ptx::mbar_wait(&hfull[hh % Pair2::kHand], (hh / Pair2::kHand) & 1u);
-                                ++hh;
-                                if (prof) ic[2] += clock64() - t0;
-                            } else {
-                                ptx::mbar_wait(&full[ss], pp);
-                                if (++ss == nslots) { ss = 0; pp ^= 1; }
-                                if (prof) ic[0] += clock64() - t0;
-                            }
-                            t0 = prof ? clock64() : 0;
-                            if (w.c == 0) {
-                                // logical rows first touched by this row pair: ga + 2, ga + 3 (and ga, ga + 1 at the top of an item)
-                                const int jj = 2 * w.pair_index();
-                                const uint32_t ga = (w.part == 0 ? g0A : g0B) + jj;
-                                uint64_t* te = tempty + w.part * P;
-                                for (uint32_t gl = (jj == 0 ? ga : ga + 2); gl < ga + 4; ++gl)
-                                    ptx::mbar_wait(&te[gl % P], ((gl / P) & 1u) ^ 1u);
-                                if (prof) ic[1] += clock64() - t0;
+                const int nin2B = (pair_rows(a, item) + 3) & ~1;
+                const int nB2 = nin2B >> 1, nA2 = nB2 + 1;
+                const int S = nB2 + lag;
+                int left = nA2 * nchA + nB2 * (nchA + 1);  // boxes of the item still to come (units do not span items)
+                // one box: layer L, row pair pr, chunk c; hand = B's x_k chunk from the hand-off slot; last = last chunk of the pair
+                auto box = [&](const int L, const int pr, const int c, const bool hand, const bool last, const bool last_pair) {
+                    if (!issuer) {
+                        if (ubox == 0) {
+                            // the issuer has finished unit gunit - 2: its "ready" barrier may be signalled again
+                            if (gunit >= 2) asm volatile("bar.sync %0, 64;" ::"r"(3 + par) : "memory");
+                            if (prof) { const long long t = clock64(); ic[0] += t - tp0; tp0 = t; }
+                            k = 0;
+                            my_bar = 0u;
+                        }
+                        // every barrier the unit needs, ONE PER LANE (a wait on an mbarrier completed through the async proxy costs
+                        // the waiting thread a few hundred cycles even when it completed long ago; a unit has up to 15 of them);
+                        // selects, not branches
+                        {
+                            const bool me = k == lane;
+                            const uint32_t bar_s = hand ? hfull_s + hq * 8u : full_s + static_cast<uint32_t>(ss) * 8u;
+                            my_bar = me ? bar_s : my_bar;
+                            my_par = me ? (hand ? hph : sph) : my_par;
+                            ++k;
+                        }
+                        if (c == 0) {
+                            // logical rows first touched by this row pair: +2, +3 (and +0, +1 at the top of an item)
+                            const uint32_t te_s = tempty_s + static_cast<uint32_t>(L) * P * 8u;
+#pragma unroll
+                            for (uint32_t d = 0u; d < 4u; ++d) {
+                                if (d < 2u && pr != 0) continue;
+                                uint32_t p = pos[L] + d, r = rev[L];
+                                if (p >= P) { p -= P; ++r; }
+                                const bool me = k == lane;
+                                my_bar = me ? te_s + p * 8u : my_bar;
+                                my_par = me ? ((r & 1u) ^ 1u) : my_par;
+                                ++k;
                             }
                         }
-                        ptx::tc_fence_after();
-                        const long long t1 = prof ? clock64() : 0;
-                        if (gunit > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
-                        if (prof) ic[3] += clock64() - t1;
-                    }
-                    const long long t2 = prof ? clock64() : 0;
-                    if (ptx::elect_one()) {
-                        Pair2Iter w = it;
-                        int ss = s;
-                        uint32_t hh = hcnt;
-                        for (int i = 0; i < cnt; ++i, w.next()) {
-                            const int L = w.part;
-                            const int jj = 2 * w.pair_index();
-                            const uint32_t ga = (L == 0 ? g0A : g0B) + jj;
-                            const uint32_t s0 = ga % P, s1 = (ga + 1) % P;
+                    } else {
+                        if (ubox == 0) {
+                            asm volatile("bar.sync %0, 64;" ::"r"(1 + par) : "memory");
+                            ptx::tc_fence_after();
+                            if (prof) { const long long t = clock64(); ic[0] += t - tp0; tp0 = t; }
+                        }
+                        if (ptx::elect_one()) {
+                            const uint32_t s0 = pos[L], s1 = s0 + 1 >= P ? s0 + 1 - P : s0 + 1;
                             const uint32_t tb = tmem_base + L * Pair2::kRingCols;
-                            const bool hand = w.hand();
-                            if (mine) {
-                                const uint8_t* aslot = hand ? hand0 + (hh % Pair2::kHand) * T::kASlot : slot0 + ss * T::kASlot;
-                                const uint8_t* bw = (L == 0 ? smem : wB) + w.c * T::kBHalf;
-                                if (!skip_mma) pair_issue_box<N>(tb + s0 * N, tb + s1 * N, ptx::smem_u32(aslot) >> 4, ptx::smem_u32(bw) >> 4);
-                                ptx::umma_commit_pair(hand ? &hempty[hh % Pair2::kHand] : &empty[ss]);
-                            }
-                            if (w.last_chunk()) {
+                            if (!skip_mma)
+                                pair_issue_box<N>(tb + s0 * N, tb + s1 * N, hand ? hand0_lo + hq * kSlotLo : slot0_lo + ss * kSlotLo,
+                                                  (L == 0 ? wA_lo : wB_lo) + c * kBHalfLo);
+                            ptx::umma_commit_pair(hand ? &hempty[hq] : &empty[ss]);
+                            if (last) {
                                 uint64_t* tf = tfull + L * P;
                                 ptx::umma_commit_pair(&tf[s0]);
                                 ptx::umma_commit_pair(&tf[s1]);
-                                if (jj + 2 >= (L == 0 ? nin2A : nin2B)) {
-                                    ptx::umma_commit_pair(&tf[(ga + 2) % P]);
-                                    ptx::umma_commit_pair(&tf[(ga + 3) % P]);
+                                if (last_pair) {
+                                    const uint32_t s2 = s0 + 2 >= P ? s0 + 2 - P : s0 + 2, s3 = s0 + 3 >= P ? s0 + 3 - P : s0 + 3;
+                                    ptx::umma_commit_pair(&tf[s2]);
+                                    ptx::umma_commit_pair(&tf[s3]);
                                 }
                             }
-                            if (hand) ++hh;
-                            else if (++ss == nslots) ss = 0;
                         }
                     }
-                    __syncwarp();
-                    if (prof && mine) ic[4] += clock64() - t2;
-                    if (mine) asm volatile("bar.arrive %0, 64;" ::"r"(2 - mw) : "memory");
-                    for (int i = 0; i < cnt; ++i, it.next()) {
-                        if (it.hand()) ++hcnt;
-                        else if (++s == nslots) { s = 0; ph ^= 1; }
+                    // advance the state both warps share by construction
+                    if (hand) {
+                        if (++hq == Pair2::kHand) { hq = 0; hph ^= 1u; }
+                    } else if (++ss == nslots) {
+                        ss = 0;
+                        sph ^= 1u;
+                    }
+                    if (last) {
+                        // the next pair of this layer starts two logical rows further; after an item's last pair the 2 trailing
+                        // phantom rows are skipped as well (an item spans nin2 + 2 logical rows)
+                        pos[L] += last_pair ? 4u : 2u;
+                        if (pos[L] >= P) { pos[L] -= P; ++rev[L]; }
+                    }
+                    --left;
+                    if (++ubox == unit || left == 0) {
+                        if (!issuer) {
+                            if (prof) { const long long t = clock64(); ic[2] += t - tp0; tp0 = t; }
+                            if (my_bar) ptx::mbar_wait_s(my_bar, my_par);
+                            __syncwarp();
+                            if (prof) { const long long t = clock64(); ic[1] += t - tp0; tp0 = t; }
+                            asm volatile("bar.arrive %0, 64;" ::"r"(1 + par) : "memory");
+                        } else {
+                            __syncwarp();
+                            if (prof) { const long long t = clock64(); ic[1] += t - tp0; tp0 = t; }
+                            asm volatile("bar.arrive %0, 64;" ::"r"(3 + par) : "memory");
+                        }
+                        ubox = 0;
+                        ++gunit;
+                        par ^= 1;
+                    }
+                };
+                for (int st = 0; st < S; ++st) {
+                    if (st < nA2) {
+                        for (int c = 0; c < nchA; ++c) box(0, st, c, false, c == nchA - 1, st == nA2 - 1);
+                    }
+                    const int bq = st - lag;
+                    if (bq >= 0 && bq < nB2) {
+                        for (int c = 0; c < nchA; ++c) box(1, bq, c, false, false, false);
+                        box(1, bq, nchA, true, true, bq == nB2 - 1);
                     }
                 }
-                g0A += nin2A + 2;
-                g0B += nin2B + 2;
             }
-            // the last unit's arrive has no matching sync: consume it so no named barrier is left half-arrived
-            if (gunit > 0 && (gunit & 1) == mw) asm volatile("bar.sync %0, 64;" ::"r"(1 + mw) : "memory");
+            // the issuer's "done" arrivals of the last two units have no matching sync yet: consume them so that no named
+            // barrier is left half-arrived
+            if (!issuer)
+                for (int u = gunit >= 2 ? gunit - 2 : 0; u < gunit; ++u) asm volatile("bar.sync %0, 64;" ::"r"(3 + (u & 1)) : "memory");
             if (prof && lane == 0) {
-                for (int i = 0; i < 5; ++i) a.dbg_cycles[310 + mw * 8 + i] = ic[i];
-                a.dbg_cycles[310 + mw * 8 + 5] = clock64() - t_start;
-                a.dbg_cycles[310 + mw * 8 + 6] = gunit;
+                const int o = 310 + (issuer ? 0 : 8);
+                for (int i = 0; i < 3; ++i) a.dbg_cycles[o + i] = ic[i];
+                a.dbg_cycles[o + 3] = clock64() - t_loop;   // main loop only (no prologue)
+                a.dbg_cycles[o + 4] = gunit;
+                a.dbg_cycles[o + 5] = t_loop - t_start;     // prologue incl. the wait for the previous launch
             }
         }
     } else {
-        // ===================== epilogue warps (both CTAs): warp % 4 = TMEM lane quarter, warp / 4 = row group =====================
+        // ===================== epilogue warps (both CTAs): warp % 4 = TMEM lane quarter; warp / 4 = group: groups 0, 1 drain layer
+        // A's even / odd logical rows, groups 2, 3 layer B's -- four rows in flight per CTA. The 32-channel layers are bound by the
+        // epilogue's serial latency chain per row (tfull -> tcgen05.ld -> tcgen05.st re-init -> hand-off / stores: ~1.2 us per row
+        // and warp, measured with the wait-cycle counters), not by its instruction count, so more rows in flight is what helps.
         const int quarter = warp & 3;
-        const uint32_t rgrp = warp >> 2;
+        const int myL = warp >> 3;
+        const uint32_t rgrp = (warp >> 2) & 1;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t lead_tempty = ptx::map_to_rank(&tempty[0], 0);
         const uint32_t lead_hfull = ptx::map_to_rank(&hfull[0], 0);
@@ -361,11 +421,41 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                 const uint32_t gl = (L == 0 ? g0A : g0B) + l;
                 const uint32_t m = gl % P;
                 const long long te0 = prof ? clock64() : 0;
-                ptx::mbar_wait(&tfull[L * P + m], (gl / P) & 1u);
+                {
+                    // the two barriers a hand-off row needs (accumulators complete, hand-off slot free) are waited for by two
+                    // different lanes at once: each such wait costs a few hundred cycles however long ago it completed
+                    const int jb = l - 2;
+                    const bool ho = L == 0 && jb >= 0 && jb < nin2B && !(a.flags & FLAG_SKIP_A);
+                    const uint32_t f = hbase + static_cast<uint32_t>(jb >> 1);
+                    if (ho && lane == 1) ptx::mbar_wait(&hempty[f % Pair2::kHand], ((f / Pair2::kHand) & 1u) ^ 1u);
+                    else if (lane == 0 || !ho) ptx::mbar_wait(&tfull[L * P + m], (gl / P) & 1u);
+                    __syncwarp();
+                }
                 if (prof) { ec[0] += clock64() - te0; ec[2] += 1; }
                 ptx::tc_fence_after();
                 const uint32_t t_main = tmem_base + lane_base + L * Pair2::kRingCols + m * N;
                 const uint32_t t_mir = m < 2 ? tmem_base + lane_base + L * Pair2::kRingCols + (P + m) * N : 0xffffffffu;
+                // image row of this logical row: A's band starts one row above B's
+                const int y = L == 0 ? y0 - 3 + l : y0 - 2 + l;
+                const int jB = l - 2;  // layer A: the B input row this x_k row is
+                const bool handoff = L == 0 && jB >= 0 && jB < nin2B;
+                const bool real = l >= 2 && l < (L == 0 ? nrow + 4 : nrow + 2);
+                if (a.flags & FLAG_SKIP_A) {  // ablation: barrier protocol only (no TMEM loads / re-initialisation, no data)
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(lead_tempty + (L * P + m) * 8);
+                    if (handoff) {
+                        const uint32_t f = hbase + static_cast<uint32_t>(jB >> 1);
+                        const uint32_t q = f % Pair2::kHand;
+                        ptx::mbar_wait(&hempty[q], ((f / Pair2::kHand) & 1u) ^ 1u);
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive_cluster(lead_hfull + q * 8);
+                    }
+                    return;
+                }
+                if (!handoff && !real) {  // phantom row: nothing to read, only hand the ring position back
+                    pair_release<N>(t_main, t_mir, s_bias[L], lane, lead_tempty + (L * P + m) * 8);
+                    return;
+                }
                 float v[32];
                 if (t_mir != 0xffffffffu) {
                     uint32_t r0[32], r1[32];
@@ -379,12 +469,6 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                     ptx::tmem_ld32(t_main, v);
                 }
                 pair_release<N>(t_main, t_mir, s_bias[L], lane, lead_tempty + (L * P + m) * 8);
-                // image row of this logical row: A's band starts one row above B's
-                const int y = L == 0 ? y0 - 3 + l : y0 - 2 + l;
-                const int jB = l - 2;  // layer A: the B input row this x_k row is
-                const bool handoff = L == 0 && jB >= 0 && jB < nin2B;
-                const bool real = l >= 2 && l < (L == 0 ? nrow + 4 : nrow + 2);
-                if (!handoff && !real) return;
                 bool zero = !x_in || xgap || y < 0 || y >= a.H || !real;
                 if (!zero)
                     for (int j = 0; j < a.ngy; ++j) zero |= ((y >> a.gshift) == a.gy[j]);
@@ -400,9 +484,7 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                 } else if (handoff) {
                     const uint32_t f = hbase + static_cast<uint32_t>(jB >> 1);
                     const uint32_t q = f % Pair2::kHand;
-                    const long long th0 = prof ? clock64() : 0;
-                    ptx::mbar_wait(&hempty[q], ((f / Pair2::kHand) & 1u) ^ 1u);
-                    if (prof) ec[1] += clock64() - th0;
+                    // (hempty[q] was waited for by lane 1 together with the accumulator-ready barrier)
                     hand_store(hand_s + q * T::kASlot, jB & 1, 1 + local, h0, h1, h2, h3);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -417,30 +499,27 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                     ptx::stg256(o + 16, h2, h3);
                 }
             };
-            for (int s = 0; s < S; ++s) {
-                if (s < nA2) {
-                    do_row(0, 2 * s + static_cast<int>(rgrp));
-                    if (s == nA2 - 1) do_row(0, nin2A + static_cast<int>(rgrp));
-                }
-                const int b = s - lag;
-                if (b >= 0 && b < nB2) {
-                    do_row(1, 2 * b + static_cast<int>(rgrp));
-                    if (b == nB2 - 1) do_row(1, nin2B + static_cast<int>(rgrp));
-                }
+            (void)S;
+            if (myL == 0) {
+                for (int s = 0; s < nA2; ++s) do_row(0, 2 * s + static_cast<int>(rgrp));
+                do_row(0, nin2A + static_cast<int>(rgrp));
+            } else {
+                for (int b = 0; b < nB2; ++b) do_row(1, 2 * b + static_cast<int>(rgrp));
+                do_row(1, nin2B + static_cast<int>(rgrp));
             }
             g0A += nin2A + 2;
             g0B += nin2B + 2;
             hbase += static_cast<uint32_t>(nB2);
         }
-        if (prof && lane == 0 && (warp == 0 || warp == 4)) {
-            for (int i = 0; i < 3; ++i) a.dbg_cycles[330 + (warp >> 2) * 4 + i] = ec[i];
-            a.dbg_cycles[330 + (warp >> 2) * 4 + 3] = clock64() - t_start;
+        if (prof && lane == 0 && (warp == 0 || warp == 8)) {
+            for (int i = 0; i < 3; ++i) a.dbg_cycles[330 + (warp >> 3) * 4 + i] = ec[i];
+            a.dbg_cycles[330 + (warp >> 3) * 4 + 3] = clock64() - t_start;
         }
     }
 
     ptx::tc_fence_before();
     ptx::cluster_sync();  // the peer may still be read (operands) or signalled (barriers) until both are done
-    if (warp == T::kEpi) {
+    if (warp == Pair2::kEpi) {
         __syncwarp();
         ptx::tmem_dealloc_pair<512>(tmem_base);
     }

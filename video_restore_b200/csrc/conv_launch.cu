@@ -385,8 +385,12 @@ static int launch_pair2(Device& dev, const CUtensorMap& tm, ConvArgs a, const Co
     a.wpack2 = wb.wpair;
     a.bias2 = wb.bias;
     a.nstages = nslots;
-    a.unit = dev.pair_unit > 0 && dev.pair_unit <= 3 ? dev.pair_unit : 2;
+    a.unit = dev.pair_unit > 0 && dev.pair_unit <= 3 ? dev.pair_unit : 3;  // measured: 1 box per hand-over +10 %, 2 +2 %, 3 best
     a.lag = dev.k4_lag >= 2 && dev.k4_lag <= 4 ? dev.k4_lag : 0;
+    // a unit is waited for as a whole before any of its boxes is issued, so it must not hold row pairs p and p + 2 of one layer
+    // (pair p + 2 re-uses ring positions pair p still occupies): with a single-chunk layer A the first steps of an item are
+    // A_0, A_1, A_2 back to back
+    if (wa.nchunks == 1 && a.unit > 2) a.unit = 2;
     if (a.unit > nslots) a.unit = nslots;
     a.tiles_x = (a.W + Pair2::kStrip - 1) / Pair2::kStrip;
     const int max_clusters = dev.sm_count / 2;

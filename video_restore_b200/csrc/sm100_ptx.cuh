@@ -49,6 +49,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// the same on a shared-memory ADDRESS (lets a lane pick its barrier with selects instead of divergent branches)
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity) {
+    auto try_wait = [&]() {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar_s), "r"(parity)
+            : "memory");
+        return ok != 0;
+    };
+    if (try_wait()) return;
+    const long long t0 = clock64();
+    while (!try_wait()) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
