@@ -303,7 +303,7 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
                         mc.gy[i] = h->gaps.gy[i];
                     }
                     VR_TRY(run_conv(h->dev, mc));
-                } else if (conv_supports_pair2(h->dev) && band >= nh) {
+                } else if (conv_supports_pair2(h->dev, nw) && band >= nh) {
                     // K4: conv1 + conv2 and conv3 + conv4 as two launches; the second layer of each pair reads x .. x_{k-1} from
                     // L2 and x_k from shared memory instead of HBM (26 -> 18 plane transfers per dense block)
                     for (int k = 1; k <= 3; k += 2) {

@@ -414,7 +414,10 @@ static int launch_pair2(Device& dev, const CUtensorMap& tm, ConvArgs a, const Co
     return 0;
 }
 
-bool conv_supports_pair2(const Device& dev) { return dev.fuse_pairs && dev.planar && (dev.rolling & 8); }
+bool conv_supports_pair2(const Device& dev, int width) {
+    if (!dev.fuse_pairs || !dev.planar || !(dev.rolling & 8)) return false;
+    return dev.fuse_pairs >= 2 || (width + Pair2::kStrip - 1) / Pair2::kStrip == (width + 127) / 128;
+}
 
 bool conv_supports_out2(const Device& dev, int cout) {
     return dev.epi_direct && ((cout == 32 && (dev.rolling & 8)) || (cout == 64 && (dev.rolling & 16)));

@@ -119,7 +119,7 @@ struct Device {
     // hand-over (0 = automatic); VR_L2HINT / VR_L2FRAC cache-policy experiments (ConvArgs::l2_hint)
     int epi_direct = 1;
     int k4_lag = 0;       // VR_K4_LAG: K4's row-pair lag of layer B (0 = default)
-    int fuse_pairs = 1;   // VR_K4=0: conv1+conv2 / conv3+conv4 of a dense block as separate K3 launches (A/B runs)
+    int fuse_pairs = 1;   // VR_K4: 0 = conv1+conv2 / conv3+conv4 as separate K3 launches, 1 = K4 where it costs no extra strip, 2 = always
     int early64 = 2;
     int pair_unit = 0;
     int l2_hint = 0;
@@ -132,7 +132,10 @@ int pack_conv_weights(Device& dev, const float* w_oihw, const float* bias, const
                       ConvWeights* out, int kc = 0);  // kc = 0: default (env VR_KC or 32)
 void free_conv_weights(ConvWeights* w);
 int run_conv(Device& dev, const ConvCall& c);
-bool conv_supports_pair2(const Device& dev);  // K4 is enabled (VR_K4, default on) and its prerequisites (K3, planar tensors) hold
+// K4 is enabled and its prerequisites (K3, chunk-planar tensors) hold. VR_K4 = 1 (default): only where its 126-pixel strips do not
+// cost an extra strip over K3's 128 (the 6-tile atlas: 13 vs 13; 1280 wide: 11 vs 10, where the extra 10 % of MMA work eats the gain);
+// 2: always; 0: never
+bool conv_supports_pair2(const Device& dev, int width);
 bool conv_supports_out2(const Device& dev, int cout);  // the configured kernel for a `cout`-channel NHWC layer takes ConvCall::out2
 // reads every conv-related environment switch into `dev` (called when a handle / test device is created, so that one
 // process can run several configurations)
