@@ -442,7 +442,21 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     total_ms_avg, conv_ms_avg = r.last_timing()
     timed_frames = r.last_timing_frames()
-    boundary_ms = exch["ms"]
+    boundary_ms = exch["ms"]   # in situ: includes waiting for a slower neighbour to reach the end of ITS range (rank skew)
+    # the transfer on its own: every rank enters together (barrier), same buffers, same grouped isend / irecv
+    transfer_ms = 0.0
+    if deferred:
+        barrier()
+        t0 = time.perf_counter()
+        ops = []
+        if d_recv is not None:
+            ops.append(dist.P2POp(dist.irecv, d_recv, rank - 1))
+        if d_send is not None:
+            ops.append(dist.P2POp(dist.isend, d_send, rank + 1))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        torch.cuda.current_stream().synchronize()
+        transfer_ms = (time.perf_counter() - t0) * 1e3
 
     # ---- end to end through the public API: host frames in, host frames out ----
     # FrameRangeSharder.run_stream -> FrameRestorer.process_stream (vr_submit / vr_wait): every frame is copied host -> device
@@ -465,9 +479,10 @@ def main():
         barrier()
 
     if dist is not None:
-        t = torch.tensor([dev_ms, e2e_ms or 0.0, boundary_ms, conv_ms_avg, total_ms_avg], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_ms or 0.0, boundary_ms, conv_ms_avg, total_ms_avg, transfer_ms], device="cuda",
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_max, boundary_ms, conv_ms_avg, total_ms_avg = [float(x) for x in t.tolist()]
+        dev_ms, e2e_max, boundary_ms, conv_ms_avg, total_ms_avg, transfer_ms = [float(x) for x in t.tolist()]
         e2e_ms = e2e_max if e2e_ms is not None else None
         lt = torch.tensor([launches, K], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
@@ -527,13 +542,19 @@ def main():
                      "hbm": hbm_side,
                      "useful_tflops_whole_step": useful / (dev_ms / max(K, 1) / 1e3) / 1e12},
         "boundary_exchange_ms": boundary_ms,
-        "multi_gpu": {"boundary_exchange_ms": boundary_ms, "inside_timed_region": bool(deferred),
+        "boundary_transfer_ms": transfer_ms,
+        "multi_gpu": {"boundary_exchange_ms": boundary_ms, "boundary_transfer_ms": transfer_ms,
+                      "note": "exchange = in situ at the end of each rank's range, inside the timed region: transfer + head-frame "
+                              "blend + waiting for a slower left neighbour (rank skew); transfer = the same grouped isend/irecv "
+                              "entered by all ranks together after a barrier (max over ranks)",
+                      "inside_timed_region": bool(deferred),
                       "protocol": "contiguous frame ranges; last un-blended frame -> rank+1 by one grouped NCCL isend/irecv "
                                   "(device to device, all ranks concurrently) + one temporal kernel on the head frame"
                                   if deferred else "no exchange (single shard or temporal stage off)",
                       "frames_total": frames_all},
     }
     config["boundary_exchange_ms"] = round(boundary_ms, 3)
+    config["boundary_transfer_ms"] = round(transfer_ms, 3)
     if e2e_ms is not None:
         n_e2e = args.frames if strong else world * K
         line["e2e"] = {"value": n_e2e / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": H * W * 3,

@@ -211,27 +211,39 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
             int s = 0;
             uint32_t ph = 0;
             long long pc[1] = {0};
+            // plain nested loops with incremental state (the generic box iterator cost this single thread ~600 cycles per box --
+            // as much as the MMAs of a box take -- so the loads of a step were issued barely faster than they were consumed)
+            const bool planar_src = a.in_cstride == 32;
+            auto load_box = [&](const int xc, const int yrow, const int c) {
+                const long long tw0 = prof ? clock64() : 0;
+                ptx::mbar_wait(&empty[s], ph ^ 1);
+                if (prof) pc[0] += clock64() - tw0;
+                if (a.flags & FLAG_SKIP_TMA) {  // ablation: the slot protocol without the loads
+                    if (rank == 0) ptx::mbar_arrive(&full[s]);
+                } else {
+                    if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
+                    const int ch0 = a.cin_off + c * T::KC;
+                    ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, planar_src ? 0 : ch0, xc, yrow,
+                                          planar_src ? ch0 >> 5 : 0);
+                }
+                if (++s == nslots) { s = 0; ph ^= 1; }
+            };
             for (int item = cluster_id; item < num_items; item += nclusters) {
                 const PairSub me = pair2_sub(a, 2 * item + static_cast<int>(rank));
                 const int xc = me.sx * Pair2::kStrip - 2;  // box column 0: one pixel left of the strip's first (halo) pixel
-                Pair2Iter it;
-                it.init((pair_rows(a, item) + 3) & ~1, nchA, lag);
-                for (; !it.done(); it.next()) {
-                    if (it.hand()) continue;
-                    // A's input rows start one row above B's: A computes the band plus a halo row on either side
-                    const int yrow = it.part == 0 ? me.y0 - 2 + 2 * it.s : me.y0 - 1 + 2 * (it.s - lag);
-                    const long long tw0 = prof ? clock64() : 0;
-                    ptx::mbar_wait(&empty[s], ph ^ 1);
-                    if (prof) pc[0] += clock64() - tw0;
-                    if (a.flags & FLAG_SKIP_TMA) {  // ablation: the slot protocol without the loads
-                        if (rank == 0) ptx::mbar_arrive(&full[s]);
-                    } else {
-                        if (rank == 0) ptx::mbar_expect_tx(&full[s], 2 * T::kCopyBytes);
-                        const int ch0 = a.cin_off + it.c * T::KC;
-                        ptx::tma_load_4d_pair(slot0 + s * T::kASlot, &tmap, lead_full + s * 8, a.in_cstride == 32 ? 0 : ch0, xc, yrow,
-                                              a.in_cstride == 32 ? ch0 >> 5 : 0);
+                const int nB2 = ((pair_rows(a, item) + 3) & ~1) >> 1, nA2 = nB2 + 1;
+                const int S = nB2 + lag;
+                // A's input rows start one row above B's: A computes the band plus a halo row on either side
+                int ya = me.y0 - 2, yb = me.y0 - 1;
+                for (int st = 0; st < S; ++st) {
+                    if (st < nA2) {
+                        for (int c = 0; c < nchA; ++c) load_box(xc, ya, c);
+                        ya += 2;
                     }
-                    if (++s == nslots) { s = 0; ph ^= 1; }
+                    if (st >= lag && st - lag < nB2) {
+                        for (int c = 0; c < nchA; ++c) load_box(xc, yb, c);
+                        yb += 2;
+                    }
                 }
             }
             if (prof) {
