@@ -8,7 +8,8 @@ Differences from upstream, all deliberate and behaviour-preserving for the refer
   * device is always CPU, half=False (fp32) -- this is "the reference's PyTorch CPU path" of the north star;
   * only the 3-channel uint8 BGR branch of `enhance` is restated (the reference feeds bgr24 frames,
     video_upscaler.py:232,246); gray / RGBA / 16-bit branches are out of scope;
-  * `outscale != scale` (Lanczos resize) is out of scope: the reference always passes outscale == scale (:501,:718);
+  * `outscale != scale` is upstream's last step, a cv2 INTER_LANCZOS4 resize of the uint8 result, restated at the end of
+    `enhance` (the reference itself always passes outscale == scale, :501,:718);
   * an extra, opt-in `blend="gaussian"` mode implements the README-only seamless tile blending
     (README.md:8,236; definition: SURVEY.md 8 A7) -- not part of upstream.
 """

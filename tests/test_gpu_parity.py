@@ -480,6 +480,13 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
         assert np.array_equal(k4, run({"VR_K4": "2", **env})[0]), env
     d = np.abs(k4.astype(np.int32) - k3.astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 3e-2
+    # smaller tile-atlas groups (VR_ATLAS_TILES bounds activation memory like --tile-size does in the reference): the grid is run
+    # as several atlases. K1 is position-independent: bit-identical; the rolling-row kernels within one level
+    assert np.array_equal(base, run({"VR_ROLL": "0", "VR_ATLAS_TILES": "1"})[0])
+    assert np.array_equal(base, run({"VR_ROLL": "0", "VR_ATLAS_TILES": "2"})[0])
+    g2 = run({"VR_ATLAS_TILES": "2"})[0]
+    d = np.abs(g2.astype(np.int32) - k4.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 3e-2
     # a different issuer hand-over granularity moves the points where the two issuing warps alternate; MMAs of different
     # warps into one accumulator are applied in a different order then (measured: not bit-identical), within tolerance
     u1 = run({"VR_K4": "0", "VR_UNIT": "1"})[0]

@@ -1,4 +1,5 @@
-"""In-tree build of libvrb200.so (the C-ABI shared library) and the oracle's C helper, with nvcc / gcc.
+"""In-tree build of libvrb200.so (the C-ABI shared library) with nvcc. (The oracle is pure Python / numpy / torch -- the
+reference is Python -- so there is nothing else to compile; `--prof` builds an instrumented second library.)
 
 `python -m video_restore_b200.build` or `__graft_entry__.build()`. Cross-compiles for sm_100a without a GPU.
 Objects are rebuilt only when a source or header is newer than the object.

@@ -75,6 +75,7 @@ struct vr_handle {
     std::map<std::string, RawTensor> raw;
     std::map<std::string, ConvWeights> layers;
     bool committed = false;
+    int atlas_tiles = 8;  // tiles per atlas axis (VR_ATLAS_TILES, read at vr_create)
     Gaps gaps;        // atlas gap mask of the frame being processed (read by conv())
     int gap_shift = 0;  // log2 of the current layer's resolution multiple
     int atlas_w = 0, atlas_h = 0;
@@ -470,13 +471,16 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
             return fail(h, VR_E_INVALID,
                         "x2 model: padded tile extent must be even (pixel_unshuffle); use an even tile size/overlap");
     }
-    const int groups_x = (tiles_x + 7) / 8, groups_y = (tiles_y + 7) / 8;
+    // VR_ATLAS_TILES (1..8, default 8): tiles per atlas axis. Activation memory is proportional to the atlas, not to the frame: a
+    // smaller group bounds it the way `--tile-size` bounds it in the reference (same result, more launches).
+    const int kGroup = h->atlas_tiles;
+    const int groups_x = (tiles_x + kGroup - 1) / kGroup, groups_y = (tiles_y + kGroup - 1) / kGroup;
     if (h->tile_out.size() < static_cast<size_t>(groups_x) * groups_y) h->tile_out.resize(static_cast<size_t>(groups_x) * groups_y);
     std::vector<BlendTile> btiles(blend ? grid.size() : 0);
     for (int gy = 0; gy < groups_y; ++gy)
         for (int gx = 0; gx < groups_x; ++gx) {
-            const int tx0 = gx * 8, ty0 = gy * 8;
-            const int ntx = std::min(8, tiles_x - tx0), nty = std::min(8, tiles_y - ty0);
+            const int tx0 = gx * kGroup, ty0 = gy * kGroup;
+            const int ntx = std::min(kGroup, tiles_x - tx0), nty = std::min(kGroup, tiles_y - ty0);
             int colw[8], rowh[8], ax0[8], ay0[8];
             for (int j = 0; j < ntx; ++j) {
                 const TileRect& t = grid[static_cast<size_t>(ty0) * tiles_x + tx0 + j];
@@ -688,6 +692,10 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
         std::fprintf(stderr, "[vrb200] VR_L2PERSIST: max %d MB, set %zu MB (%s)\n", max_persist >> 20, want >> 20, cudaGetErrorString(pe));
     }
     read_conv_env(h->dev);
+    if (const char* e = std::getenv("VR_ATLAS_TILES")) {
+        const int v = std::atoi(e);
+        h->atlas_tiles = v < 1 ? 1 : (v > 8 ? 8 : v);
+    }
     if (const char* e = std::getenv("VR_PLANAR")) h->dev.planar = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;

@@ -474,23 +474,27 @@ clahe_hist_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int W
     if (s_hist[threadIdx.x]) atomicAdd(&hist[tile * 256 + threadIdx.x], static_cast<int>(s_hist[threadIdx.x]));
 }
 // pass 2: clip, redistribute, prefix sum, LUT. One 256-thread block per tile. Integer work: bit-exact.
+// Both reductions are warp-shuffle based: the clipped excess is summed with __shfl_down_sync (one shared-memory word per warp
+// instead of up to 256 atomics on one), the 256-bin cumulative histogram is an intra-warp __shfl_up_sync scan plus the eight
+// warp totals (two block barriers instead of the sixteen of a shared-memory Hillis-Steele scan).
 __global__ void __launch_bounds__(256)
 clahe_lut_kernel(int32_t* __restrict__ hist, uint8_t* __restrict__ lut, int clip, float lut_scale) {
-    __shared__ int s[256];
-    __shared__ int s_clipped;
-    const int t = threadIdx.x, tile = blockIdx.x;
+    __shared__ int s_wsum[8];   // per-warp clipped excess
+    __shared__ int s_wtot[8];   // per-warp histogram totals (scan)
+    const int t = threadIdx.x, tile = blockIdx.x, lane = t & 31, warp = t >> 5;
     int h = hist[tile * 256 + t];
-    if (t == 0) s_clipped = 0;
-    __syncthreads();
     if (clip > 0) {
-        if (h > clip) {
-            atomicAdd(&s_clipped, h - clip);
-            h = clip;
-        }
+        int ex = h > clip ? h - clip : 0;
+        if (h > clip) h = clip;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ex += __shfl_down_sync(0xffffffffu, ex, off);
+        if (lane == 0) s_wsum[warp] = ex;
         __syncthreads();
-        const int clipped = s_clipped;
+        int clipped = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) clipped += s_wsum[w];
         const int batch = clipped / 256;
-        int residual = clipped - batch * 256;
+        const int residual = clipped - batch * 256;
         h += batch;
         if (residual != 0) {
             const int step = max(256 / residual, 1);
@@ -498,15 +502,16 @@ clahe_lut_kernel(int32_t* __restrict__ hist, uint8_t* __restrict__ lut, int clip
         }
     }
     hist[tile * 256 + t] = h;
-    s[t] = h;
-    __syncthreads();
-    for (int off = 1; off < 256; off <<= 1) {  // Hillis-Steele inclusive scan
-        const int v = t >= off ? s[t - off] : 0;
-        __syncthreads();
-        s[t] += v;
-        __syncthreads();
+    int c = h;  // inclusive scan inside the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, c, off);
+        if (lane >= off) c += v;
     }
-    const int q = __float2int_rn(__fmul_rn(static_cast<float>(s[t]), lut_scale));
+    if (lane == 31) s_wtot[warp] = c;
+    __syncthreads();
+    for (int w = 0; w < warp; ++w) c += s_wtot[w];
+    const int q = __float2int_rn(__fmul_rn(static_cast<float>(c), lut_scale));
     lut[tile * 256 + t] = static_cast<uint8_t>(min(max(q, 0), 255));
 }
 // pass 3: BGR -> YCrCb, bilinear LUT interpolation on Y, -> BGR

@@ -340,8 +340,12 @@ class BufferPool:
     (FrameRestorer.process_stream(out_pool=...)), the reassembler hands them to the sink and gives them back: no
     per-frame copy, and the host memory of the whole pipeline is bounded by count * frame bytes."""
 
-    def __init__(self, count: int, alloc: Callable):
+    def __init__(self, count: int, alloc: Callable, min_count: int = 0, max_bytes: Optional[int] = None):
+        """count: upper bound on buffers; max_bytes: soft cap on page-locked memory -- once `min_count` buffers exist (what the
+        reorder ring needs to make progress) no further buffer is allocated beyond it; callers wait for a release instead.
+        (the pool used to pin capacity + 5 G frames whatever their size, ~17 GB for 8 GPUs at 4K output.)"""
         self.count, self._alloc = count, alloc
+        self.min_count, self.max_bytes = min_count, max_bytes
         self._cv = threading.Condition()
         self._free: List[np.ndarray] = []
         self.allocated = 0
@@ -356,7 +360,7 @@ class BufferPool:
                 for i, b in enumerate(self._free):
                     if b.shape == shape:
                         return self._free.pop(i)
-                if self.allocated < self.count:
+                if self.allocated < self.count and self._within_bytes(shape):
                     self.allocated += 1
                     break
                 if self._free:  # another frame size (a new clip): drop a stale buffer and allocate
@@ -365,13 +369,18 @@ class BufferPool:
                 self._cv.wait(0.5)
         return self._alloc(shape)
 
+    def _within_bytes(self, shape) -> bool:
+        if self.max_bytes is None or self.allocated < max(self.min_count, 1):
+            return True
+        return (self.allocated + 1) * int(np.prod(shape)) <= self.max_bytes
+
     def reserve(self, shape, n: int) -> None:
         """Allocate up to `n` more buffers now: page-locked allocations synchronise the device(s), so a pool that grows
         while frames are in flight stalls every GPU for ~10 ms per buffer."""
         shape = tuple(shape)
         for _ in range(n):
             with self._cv:
-                if self.allocated >= self.count:
+                if self.allocated >= self.count or not self._within_bytes(shape):
                     return
                 self.allocated += 1
             buf = self._alloc(shape)
@@ -596,7 +605,11 @@ def run_pipeline(source, sink, make_restorer: Callable[[int], object], gpu_ids: 
                 with lock:
                     if pool[0] is None:
                         # ring + per worker: two frames in flight, one being handed over, the deferred head, a boundary frame
-                        pool[0] = BufferPool(capacity + 5 * G, restorer.alloc_host)
+                        # soft cap on pinned memory (VR_PINNED_MB, default 8192): never below what the ring needs to progress
+                        import os
+                        cap_mb = int(os.environ.get("VR_PINNED_MB", "8192"))
+                        pool[0] = BufferPool(capacity + 5 * G, restorer.alloc_host, min_count=need + 2 * G + 1,
+                                             max_bytes=cap_mb << 20)
             kw = {"out_pool": pool[0]} if zero_copy else {}
             give_back = pool[0].release if zero_copy else None
             if warmup and total > 0:
