@@ -463,6 +463,9 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
     assert np.array_equal(base, multi) and n_multi < n_base
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_PDL": "0"})[0])
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_WRES": "0"})[0])
+    # the four phases of each folded upsample conv as four launches instead of one launch walking all phases per input tile
+    ph4, n_ph4 = run({"VR_ROLL": "0", "VR_PHASES1": "0"})
+    assert np.array_equal(base, ph4) and n_ph4 == n_base + 6
     # K2 / K3 on their layer classes: deterministic and independent of PDL; against K1 the fp32 summation order differs (bias is the
     # accumulator's initial value, taps are summed row by row), so the 8-bit frames agree within one level
     # interleaved instead of chunk-planar activation tensors: same arithmetic in the same order
@@ -476,7 +479,7 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
         assert np.array_equal(k3, run({"VR_K4": "0", **env})[0]), env
     # the default path (K4 pairs + K3): the same switches only touch its K3 layers -- still bit-identical to itself
     k4 = run({"VR_K4": "2"})[0]
-    for env in ({"VR_EARLY64": "0"}, {"VR_EARLY64": "1"}, {"VR_PDL": "0"}):
+    for env in ({"VR_EARLY64": "0"}, {"VR_EARLY64": "1"}, {"VR_PDL": "0"}, {"VR_PHASES1": "0"}):
         assert np.array_equal(k4, run({"VR_K4": "2", **env})[0]), env
     d = np.abs(k4.astype(np.int32) - k3.astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 3e-2

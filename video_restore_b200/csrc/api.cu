@@ -181,7 +181,7 @@ void set_io(ConvCall& c, const Act& in, const Act& out) {
 int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out, int out_coff, int act, Act res1 = Act(),
          float s1 = 1.f, Act res2 = Act(), float s2 = 1.f, int out_mode = OUT_NHWC, const __half* base = nullptr,
          int base_c = 0, Rows rows = Rows(), int phase = -1, Act out2 = Act()) {
-    const ConvWeights* w = layer(h, name);
+    const ConvWeights* w = layer(h, phase == 4 ? name + ".phase0" : name);
     if (!w) return fail(h, VR_E_STATE, "missing layer " + name);
     ConvCall c;
     set_io(c, in, out);
@@ -206,7 +206,14 @@ int conv(vr_handle* h, const std::string& name, Act in, int nh, int nw, Act out,
     c.base_cstride = base_c;
     c.y_begin = rows.y0;
     c.y_end = rows.y1;
-    if (phase >= 0) {  // output phase (py, px) of a conv folded with a preceding nearest x2 upsample
+    if (phase == 4) {  // all four phases in one launch (input tiles read once; weights per phase)
+        c.dys = c.dxs = 3;
+        c.omul = 2;
+        for (int ph = 0; ph < 4; ++ph) {
+            c.lw[ph] = layer(h, name + ".phase" + std::to_string(ph));
+            if (!c.lw[ph]) return fail(h, VR_E_STATE, "missing layer " + name + ".phase" + std::to_string(ph));
+        }
+    } else if (phase >= 0) {  // output phase (py, px) of a conv folded with a preceding nearest x2 upsample
         const int py = phase >> 1, px = phase & 1;
         c.dys = py == 0 ? 1 : 2;  // py = 0 reads rows y-1, y (taps 0,1); py = 1 reads rows y, y+1 (taps 1,2)
         c.dxs = px == 0 ? 1 : 2;
@@ -353,13 +360,23 @@ int run_rrdbnet(vr_handle* h, int nh, int nw, __half* tile_out) {
     if (h->dev.fold_upsample) {
         // lrelu(conv_up(nearest_x2(f))) as four 2x2-tap convs on f itself (one per output phase, pre-summed weights):
         // no upsampled tensor, 4/9 of the MACs
-        for (int ph = 0; ph < 4; ++ph)
-            VR_TRY(conv(h, "conv_up1.phase" + std::to_string(ph), trunk, nh, nw, u1o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f,
-                        OUT_NHWC, nullptr, 0, Rows(), ph));
+        // one launch per upsample conv walks the four phases of every input tile (the input is read from HBM once, not four
+        // times); VR_PHASES1=0: four launches (bit-identical)
+        if (h->dev.fuse_phases) {
+            VR_TRY(conv(h, "conv_up1", trunk, nh, nw, u1o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f, OUT_NHWC, nullptr, 0, Rows(), 4));
+        } else {
+            for (int ph = 0; ph < 4; ++ph)
+                VR_TRY(conv(h, "conv_up1.phase" + std::to_string(ph), trunk, nh, nw, u1o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f,
+                            OUT_NHWC, nullptr, 0, Rows(), ph));
+        }
         h->gap_shift = 1;  // the phases of conv_up2 run on the 2x grid: gap columns / rows are 2 pixels wide there
-        for (int ph = 0; ph < 4; ++ph)
-            VR_TRY(conv(h, "conv_up2.phase" + std::to_string(ph), u1o, 2 * nh, 2 * nw, u2o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f,
-                        OUT_NHWC, nullptr, 0, Rows(), ph));
+        if (h->dev.fuse_phases) {
+            VR_TRY(conv(h, "conv_up2", u1o, 2 * nh, 2 * nw, u2o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f, OUT_NHWC, nullptr, 0, Rows(), 4));
+        } else {
+            for (int ph = 0; ph < 4; ++ph)
+                VR_TRY(conv(h, "conv_up2.phase" + std::to_string(ph), u1o, 2 * nh, 2 * nw, u2o, 0, ACT_LRELU, Act(), 1.f, Act(), 1.f,
+                            OUT_NHWC, nullptr, 0, Rows(), ph));
+        }
         h->gap_shift = 2;
     } else {
         VR_TRY(upsample2x_act(h, trunk, nh, nw, u1i));
@@ -699,6 +716,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     if (const char* e = std::getenv("VR_PLANAR")) h->dev.planar = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_PHASES1")) h->dev.fuse_phases = std::atoi(e) != 0;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->dev.stream, cudaStreamNonBlocking) != cudaSuccess)
         return bad("cudaStreamCreate failed", VR_E_CUDA);

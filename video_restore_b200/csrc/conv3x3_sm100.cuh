@@ -207,7 +207,7 @@ __device__ __forceinline__ void bias_act(float* v, const float* s_bias, const fl
 template <int N>
 __device__ __forceinline__ void epi_row_nhwc(const ConvArgs& a, uint32_t t_addr, uint32_t stg_s, int lane, int x_base, int y,
                                              bool gap, int out_coff, int coff_add, const float* s_bias, const float* s_neg,
-                                             int amode) {
+                                             int amode, int opy, int opx) {
     constexpr int kVec = N / 8;  // 16 B units per pixel
     constexpr int kStgPitch = N * 2;
     const int x = x_base + lane;
@@ -264,7 +264,7 @@ __device__ __forceinline__ void epi_row_nhwc(const ConvArgs& a, uint32_t t_addr,
     }
     __syncwarp();
     // lane l always handles 16 B unit l % kVec of its pixels (32 % kVec == 0)
-    __half* orow = a.out + chan_off(static_cast<size_t>(y * a.omul + a.opy) * (a.W * a.omul) + x_base * a.omul + a.opx, a.out_cstride,
+    __half* orow = a.out + chan_off(static_cast<size_t>(y * a.omul + opy) * (a.W * a.omul) + x_base * a.omul + opx, a.out_cstride,
                                     a.out_pstride, out_coff + coff_add + (lane % kVec) * 8);
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
@@ -389,13 +389,58 @@ __device__ __forceinline__ void epi_row_nhwc_folded(const ConvArgs& a, uint32_t 
     __syncwarp();
 }
 
+// The MMAs of one pipeline stage (one 32- / 16-channel chunk of the haloed input tile) for the tap window dy in [kDy0, kDy1],
+// dx in [kDx0, kDx1]: dy-stacked N as described in the kernel. `first_chunk`: the lowest present tap of chunk 0 is the first
+// touch of an output row in this tile and must overwrite instead of accumulate.
+template <int N, int TH, int KC, int kDy0, int kDy1, int kDx0, int kDx1>
+__device__ __forceinline__ void conv_issue_stage(uint32_t a_lo0, uint32_t b_lo0, uint32_t d_base, bool first_chunk) {
+    using T = ConvTraits<N, TH, KC>;
+#pragma unroll
+    for (int dx = kDx0; dx <= kDx1; ++dx) {
+#pragma unroll
+        for (int k = 0; k < T::kKSteps; ++k) {
+#pragma unroll
+            for (int rho = 0; rho < T::kInRows; ++rho) {
+                const uint32_t a_lo = a_lo0 + (((rho * T::kPitch + dx) * T::kRowBytes + k * 32) >> 4);
+                constexpr int kLast = TH - 1;
+                // taps dy in [dy_lo, dy_hi] of this input row land in output rows rho - dy
+                const int lo_r = rho - kLast > 0 ? rho - kLast : 0;
+                const int hi_r = rho < 2 ? rho : 2;
+                const int dy_lo = lo_r > kDy0 ? lo_r : kDy0;
+                const int dy_hi = hi_r < kDy1 ? hi_r : kDy1;
+                if (dy_lo > dy_hi) continue;  // this input row feeds no present tap
+                const int nblk = dy_hi - dy_lo + 1;
+                const int r_lo = rho - dy_hi;
+                // B rows of this dx: [dy=2 | dy=1 | dy=0] x N
+                const uint32_t b_lo = b_lo0 + ((((dx * 3 + (2 - dy_hi)) * N) * T::kRowBytes + k * 32) >> 4);
+                const uint32_t d = d_base + r_lo * N;
+                if (dx == kDx0 && k == 0 && dy_lo == kDy0 && first_chunk) {
+                    // the lowest present tap is the first touch of output row rho - kDy0 in this
+                    // tile: it must overwrite while the other blocks accumulate -> split the MMA
+                    if (nblk > 1)
+                        ptx::umma_f16<ptx::kCollNone>(d, a_lo, T::kDescHi, b_lo, T::kDescHi,
+                                                      ptx::make_idesc_f16(128, (nblk > 1 ? nblk - 1 : 1) * N), 1u);
+                    ptx::umma_f16<ptx::kCollNone>(d + (nblk - 1) * N, a_lo, T::kDescHi,
+                                                  b_lo + (((nblk - 1) * N * T::kRowBytes) >> 4), T::kDescHi,
+                                                  ptx::make_idesc_f16(128, N), 0u);
+                } else {
+                    ptx::umma_f16<ptx::kCollNone>(d, a_lo, T::kDescHi, b_lo, T::kDescHi, ptx::make_idesc_f16(128, nblk * N), 1u);
+                }
+            }
+        }
+    }
+}
+
 // DYS / DXS select the taps that are present: 0 = all three, 1 = {0, 1}, 2 = {1, 2} (the 2x2 sub-kernels of the four
 // output phases of upsample-then-conv; the absent taps have zero weights and their MMAs are simply not issued).
 template <int N, int TH, int KC, int DYS = 0, int DXS = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
-    constexpr int kDy0 = DYS == 2 ? 1 : 0, kDy1 = DYS == 1 ? 1 : 2;  // present dy taps [kDy0, kDy1]
-    constexpr int kDx0 = DXS == 2 ? 1 : 0, kDx1 = DXS == 1 ? 1 : 2;
+    // DYS == DXS == 3: ALL FOUR phases of an upsample-folded conv in one launch. Work item = (tile, phase), phase fastest: the
+    // CTA loads the same input tile four times back to back (three of them L2 hits) instead of four launches each streaming
+    // the whole input from HBM; per phase its own pre-summed weights (a.l_wpack[phase]), tap window and output pixel offset.
+    // The MMA sequence of a phase is exactly that of the single-phase instantiation: results are bit-identical.
+    constexpr bool kAllPh = DYS == 3 && DXS == 3;
     using T = ConvTraits<N, TH, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -457,7 +502,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_slot;
     const int num_tiles = a.tiles_x * a.tiles_y;
-    const int num_items = num_tiles * a.nlayers;
+    const int num_items = kAllPh ? num_tiles * 4 : num_tiles * a.nlayers;
     if (a.wres && warp == kEpiWarps && lane == 0) {
         // weights are never written by a kernel: fetch them before waiting on the previous layer
         ptx::mbar_expect_tx(wfull, a.nchunks * T::kBBytes);
@@ -480,11 +525,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
             int pre0 = 0, pre1 = 0, pre2 = 0;
             bool pre_valid = false;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                const int layer = item / num_tiles, tile = item - layer * num_tiles;
+                const int layer = kAllPh ? 0 : item / num_tiles, tile = kAllPh ? item >> 2 : item - layer * num_tiles;
                 const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
                 const int x0 = tx * 128, y0 = a.y_begin + ty * TH;
                 const int nch = s_l_nchunks[layer];
-                const __half* wp = s_l_wpack[layer];
+                const __half* wp = kAllPh ? a.l_wpack[item & 3] : s_l_wpack[layer];
                 if (layer > 0) {
                     // rows y0-1 .. y0+TH of the previous layer = its tile rows ty-1 .. ty+1, all tile columns.
                     // The three counters were read one item ahead (pre0..2, below): normally no round trip here.
@@ -510,7 +555,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 {
                     // read the NEXT item's dependency counters now; their latency hides behind this item's loads
                     const int nitem = item + static_cast<int>(gridDim.x);
-                    if (nitem < num_items) {
+                    if (!kAllPh && nitem < num_items) {  // (an all-phase launch has no inter-layer dependencies: items are phases)
                         const int nl = nitem / num_tiles, nt = nitem - nl * num_tiles;
                         if (nl > 0) {
                             const int nty = nt / a.tiles_x;
@@ -566,7 +611,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int nch = s_l_nchunks[item / num_tiles];
+            const int nch = kAllPh ? a.nchunks : s_l_nchunks[item / num_tiles];
             ptx::mbar_wait(&tempty[buf], aph ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_base = tmem_base + buf * T::kAccCols;
@@ -583,43 +628,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                     const uint32_t a_lo0 = (ptx::smem_u32(stage0 + s * a.stage_bytes) >> 4);
                     const uint32_t b_lo0 = a.wres ? (ptx::smem_u32(smem + c * T::kBStage) >> 4) : a_lo0 + (T::kAStage >> 4);
                     if (!skip_mma) {
-#pragma unroll
-                        for (int dx = kDx0; dx <= kDx1; ++dx) {
-#pragma unroll
-                            for (int k = 0; k < T::kKSteps; ++k) {
-#pragma unroll
-                                for (int rho = 0; rho < T::kInRows; ++rho) {
-                                    const uint32_t a_lo = a_lo0 + (((rho * T::kPitch + dx) * T::kRowBytes + k * 32) >> 4);
-                                    constexpr int kLast = TH - 1;
-                                    // taps dy in [dy_lo, dy_hi] of this input row land in output rows rho - dy
-                                    const int lo_r = rho - kLast > 0 ? rho - kLast : 0;
-                                    const int hi_r = rho < 2 ? rho : 2;
-                                    const int dy_lo = lo_r > kDy0 ? lo_r : kDy0;
-                                    const int dy_hi = hi_r < kDy1 ? hi_r : kDy1;
-                                    if (dy_lo > dy_hi) continue;  // this input row feeds no present tap
-                                    const int nblk = dy_hi - dy_lo + 1;
-                                    const int r_lo = rho - dy_hi;
-                                    // B rows of this dx: [dy=2 | dy=1 | dy=0] x N
-                                    const uint32_t b_lo = b_lo0 + ((((dx * 3 + (2 - dy_hi)) * N) * T::kRowBytes + k * 32) >> 4);
-                                    const uint32_t d = d_base + r_lo * N;
-                                    if (dx == kDx0 && k == 0 && dy_lo == kDy0 && c == 0) {
-                                        // the lowest present tap is the first touch of output row rho - kDy0 in this
-                                        // tile: it must overwrite while the other blocks accumulate -> split the MMA
-                                        if (nblk > 1)
-                                            ptx::umma_f16<ptx::kCollNone>(
-                                                d, a_lo, T::kDescHi, b_lo, T::kDescHi,
-                                                ptx::make_idesc_f16(128, (nblk > 1 ? nblk - 1 : 1) * N), 1u);
-                                        ptx::umma_f16<ptx::kCollNone>(
-                                            d + (nblk - 1) * N, a_lo, T::kDescHi,
-                                            b_lo + (((nblk - 1) * N * T::kRowBytes) >> 4), T::kDescHi,
-                                            ptx::make_idesc_f16(128, N), 0u);
-                                    } else {
-                                        ptx::umma_f16<ptx::kCollNone>(d, a_lo, T::kDescHi, b_lo,
-                                                                      T::kDescHi,
-                                                                      ptx::make_idesc_f16(128, nblk * N), 1u);
-                                    }
-                                }
+                        if constexpr (kAllPh) {
+                            switch (item & 3) {  // phase (py, px): taps {0,1} for 0, {1,2} for 1
+                                case 0: conv_issue_stage<N, TH, KC, 0, 1, 0, 1>(a_lo0, b_lo0, d_base, c == 0); break;
+                                case 1: conv_issue_stage<N, TH, KC, 0, 1, 1, 2>(a_lo0, b_lo0, d_base, c == 0); break;
+                                case 2: conv_issue_stage<N, TH, KC, 1, 2, 0, 1>(a_lo0, b_lo0, d_base, c == 0); break;
+                                default: conv_issue_stage<N, TH, KC, 1, 2, 1, 2>(a_lo0, b_lo0, d_base, c == 0); break;
                             }
+                        } else {
+                            constexpr int kDy0 = DYS == 2 ? 1 : 0, kDy1 = DYS == 1 ? 1 : 2;  // present dy taps [kDy0, kDy1]
+                            constexpr int kDx0 = DXS == 2 ? 1 : 0, kDx1 = DXS == 1 ? 1 : 2;
+                            conv_issue_stage<N, TH, KC, kDy0, kDy1, kDx0, kDx1>(a_lo0, b_lo0, d_base, c == 0);
                         }
                     }
                     ptx::umma_commit(&empty[s]);
@@ -646,7 +665,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int layer = item / num_tiles, tile = item - layer * num_tiles;
+            const int layer = kAllPh ? 0 : item / num_tiles, tile = kAllPh ? item >> 2 : item - layer * num_tiles;
+            const int opy = kAllPh ? (item >> 1) & 1 : a.opy, opx = kAllPh ? item & 1 : a.opx;
             const int out_coff = s_l_out_coff[layer];
             const float* s_bias = s_bias_all[layer];
             const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
@@ -710,7 +730,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
                 } else {
                     if constexpr (N % 32 == 0) {
                         epi_row_nhwc<N>(a, t_row0 + r * N, stg_s, lane, tx * 128 + quarter * 32, y, gap, out_coff, 0, s_bias, s_neg,
-                                        amode);
+                                        amode, opy, opx);
                         __syncwarp();
                     }
                 }

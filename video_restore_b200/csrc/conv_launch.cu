@@ -205,13 +205,13 @@ static int launch_one(Device& dev, const CUtensorMap& tm, ConvArgs a) {
     }
     a.tiles_x = (a.W + 127) / 128;
     a.tiles_y = (a.y_end - a.y_begin + TH - 1) / TH;
-    const int tiles = a.tiles_x * a.tiles_y * a.nlayers;  // work items of this launch
+    const int tiles = a.tiles_x * a.tiles_y * (DYS == 3 ? 4 : a.nlayers);  // work items of this launch (x4: all phases per tile)
     const int grid = tiles < dev.sm_count ? tiles : dev.sm_count;
     // shared-memory plan: resident weights when the whole layer fits WITHOUT reducing the pipeline depth (measured:
     // +3..5 % on 64->32, 96->32, 64->64; with only 2 activation stages left, 128->32 / 160->32 lose 4..8 %)
     const int w_bytes = a.nchunks * T::kBStage;
     const int a_stages = (T::kBudget - w_bytes) / T::kAStage;
-    if (dev.weights_resident && a.nlayers == 1 && a_stages >= T::kStages) {
+    if (dev.weights_resident && a.nlayers == 1 && a_stages >= T::kStages && DYS != 3) {  // all-phase launch: weights change per item
         a.wres = 1;
         a.nstages = a_stages > kMaxStages ? kMaxStages : a_stages;
         a.stage_bytes = T::kAStage;
@@ -592,6 +592,21 @@ int run_conv(Device& dev, const ConvCall& c) {
     if (c.flags & (FLAG_FORCE_ROLL | FLAG_FORCE_PAIR)) {
         set_error(dev.err, "run_conv: the rolling-row kernels do not take this layer");
         return -1;
+    }
+    if (c.dys == 3 && c.dxs == 3) {
+        // all four phases of an upsample-folded conv in one launch: lw[0..3] = the phases' pre-summed weights
+        if (w.npad != 64 || rows != 4 || w.kc != 32 || c.nlayers != 1 || c.omul != 2 || c.out_mode != OUT_NHWC) {
+            set_error(dev.err, "run_conv: no all-phase kernel for this layer shape");
+            return -1;
+        }
+        for (int ph = 0; ph < 4; ++ph) {
+            if (!c.lw[ph] || c.lw[ph]->npad != 64 || c.lw[ph]->kc != 32 || c.lw[ph]->nchunks != w.nchunks) {
+                set_error(dev.err, "run_conv: all-phase launch needs four phase weight sets of the layer's shape");
+                return -1;
+            }
+            a.l_wpack[ph] = c.lw[ph]->wpack;
+        }
+        return launch_one<64, 4, 32, 3, 3>(dev, tm, a);
     }
     if (c.dys || c.dxs) {
         // 2x2-tap phases of an upsample-folded conv: only the 64-channel / 4-row / 32-channel-chunk family is built
