@@ -235,8 +235,23 @@ conv3x3_pair2_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                 const int S = nB2 + lag;
                 // A's input rows start one row above B's: A computes the band plus a halo row on either side
                 int ya = me.y0 - 2, yb = me.y0 - 1;
+                // Experiment, off by default (a.prefetch = 0): layer A's boxes come from HBM and the slot ring only reaches 0.75 .. 2
+                // steps ahead, so their rows can be pulled into the L2 `pf` steps early with prefetch-only TMA requests (no shared
+                // memory needed). Measured slower -- the TMA unit's request rate is the scarcer resource (see vr_common.h).
+                const int pf = a.prefetch;
+                if (pf > 0 && !(a.flags & FLAG_SKIP_TMA))
+                    for (int st = 0; st < pf && st < nA2; ++st)
+                        for (int c = 0; c < nchA; ++c) {
+                            const int ch0 = a.cin_off + c * T::KC;
+                            ptx::tma_prefetch_4d(&tmap, planar_src ? 0 : ch0, xc, ya + 2 * st, planar_src ? ch0 >> 5 : 0);
+                        }
                 for (int st = 0; st < S; ++st) {
                     if (st < nA2) {
+                        if (pf > 0 && st + pf < nA2 && !(a.flags & FLAG_SKIP_TMA))
+                            for (int c = 0; c < nchA; ++c) {
+                                const int ch0 = a.cin_off + c * T::KC;
+                                ptx::tma_prefetch_4d(&tmap, planar_src ? 0 : ch0, xc, ya + 2 * pf, planar_src ? ch0 >> 5 : 0);
+                            }
                         for (int c = 0; c < nchA; ++c) load_box(xc, ya, c);
                         ya += 2;
                     }

@@ -63,6 +63,7 @@ struct ConvArgs {
     const float* bias2;
     int out_coff2;
     int lag;               // K4: row pairs layer B runs behind layer A (0 = default 2)
+    int prefetch;          // K4: steps (row pairs) layer A's rows are prefetched into the L2 ahead of their TMA load (0 = off)
     // Chunk-planar tensors: a tensor with cstride == 32 stores channels [32k, 32k+32) as plane k, [H][W][32] fp16, planes
     // `pstride` elements apart (every TMA box row and every output row is then contiguous; the interleaved [H][W][C] form
     // costs the 32-channel layers 16..52 %). Any other cstride is the interleaved form (pstride unused).

@@ -387,6 +387,7 @@ static int launch_pair2(Device& dev, const CUtensorMap& tm, ConvArgs a, const Co
     a.nstages = nslots;
     a.unit = dev.pair_unit > 0 && dev.pair_unit <= 3 ? dev.pair_unit : 3;  // measured: 1 box per hand-over +10 %, 2 +2 %, 3 best
     a.lag = dev.k4_lag >= 2 && dev.k4_lag <= 4 ? dev.k4_lag : 0;
+    a.prefetch = dev.k4_prefetch < 0 ? 0 : (dev.k4_prefetch > 16 ? 16 : dev.k4_prefetch);
     // a unit is waited for as a whole before any of its boxes is issued, so it must not hold row pairs p and p + 2 of one layer
     // (pair p + 2 re-uses ring positions pair p still occupies): with a single-chunk layer A the first steps of an item are
     // A_0, A_1, A_2 back to back
@@ -438,6 +439,7 @@ void read_conv_env(Device& dev) {
     geti("VR_EPI_DIRECT", &dev.epi_direct);
     geti("VR_K4", &dev.fuse_pairs);
     geti("VR_K4_LAG", &dev.k4_lag);
+    geti("VR_K4_PREFETCH", &dev.k4_prefetch);
     geti("VR_EARLY64", &dev.early64);
     geti("VR_UNIT", &dev.pair_unit);
     geti("VR_L2HINT", &dev.l2_hint);

@@ -95,6 +95,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
+// L2 prefetch of a tile (no shared memory, no barrier): a later tma_load of the same box then hits the L2.
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(c3)
+                 : "memory");
+}
 // 1-D bulk copy global -> shared, completes on mbarrier. bytes % 16 == 0, both addresses 16 B aligned.
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile(

@@ -119,6 +119,10 @@ struct Device {
     // VR_EARLY64 = 0 / 1 / 2 when a 64-channel row's ring position goes back (ConvArgs::early64); VR_UNIT boxes per issuer
     // hand-over (0 = automatic); VR_L2HINT / VR_L2FRAC cache-policy experiments (ConvArgs::l2_hint)
     int epi_direct = 1;
+    // VR_K4_PREFETCH: row pairs of prefetch-only TMA requests ahead of layer A's loads. Off: measured 2 .. 14 % SLOWER, growing
+    // with the distance (profiles/r2_k4_prefetch.txt) -- the TMA unit's request rate on 64-byte rows (260 per box, ~600 cycles: what
+    // the box's 12 MMAs take) is itself near-critical on the 32-channel layers, so extra requests cost more than the latency they hide
+    int k4_prefetch = 0;
     int k4_lag = 0;       // VR_K4_LAG: K4's row-pair lag of layer B (0 = default)
     int fuse_pairs = 1;   // VR_K4: 0 = conv1+conv2 / conv3+conv4 as separate K3 launches, 1 = K4 where it costs no extra strip, 2 = always
     int early64 = 2;
