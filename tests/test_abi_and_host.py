@@ -114,3 +114,32 @@ def test_cli_enhancement_flags():
     assert config_from_args(p.parse_args(["a", "b", "--model", "RealESRGAN_x2plus"])).scale == 2
     with pytest.raises(SystemExit):
         p.parse_args(["a", "b", "--model", "nope"])
+
+
+def test_cli_missing_checkpoint_is_an_error_unless_random_weights_are_requested(tmp_path, monkeypatch, capsys):
+    """the CLI used to fall back to random-init weights silently and write a full-length video of garbage. The
+    reference downloads the checkpoint or fails (video_upscaler.py:342-367)."""
+    from video_restore_b200.cli import MissingWeights, OptimizedConfig, build_parser, load_weights
+
+    monkeypatch.chdir(tmp_path)   # no models/ directory here
+    cfg = OptimizedConfig(model_name="RealESRGAN_x4_v3")
+    with pytest.raises(MissingWeights, match="--random-weights"):
+        load_weights(cfg)
+    sd = load_weights(cfg, allow_random=True)
+    assert "body.0.weight" in sd and "not a restored video" in capsys.readouterr().out
+    args = build_parser().parse_args(["a", "b", "--random-weights", "--procs"])
+    assert args.random_weights and args.procs
+
+
+def test_frame_digests_are_order_defined():
+    import numpy as np
+
+    from video_restore_b200.multiproc import combine_digests, frame_digest
+
+    a = np.arange(64 * 32 * 3, dtype=np.uint8).reshape(64, 32, 3)
+    b = a.copy()
+    b[8, 3, 1] ^= 1            # row 8 is one of the sampled rows (every 8th)
+    assert frame_digest(a) != frame_digest(b)
+    d1 = {0: frame_digest(a), 1: frame_digest(b)}
+    d2 = {1: frame_digest(b), 0: frame_digest(a)}      # arrival order of the ranks does not matter
+    assert combine_digests(d1) == combine_digests(d2) != combine_digests({0: d1[1], 1: d1[0]})

@@ -376,3 +376,23 @@ def test_restorer_construction_failure_propagates():
 
     with pytest.raises(ValueError, match="no such device"):
         run_pipeline(ArraySource(clip(10)), NullSink(), make, [0, 1, 2], FrameOpts(temporal=True), chunk=2, temporal_blend=stub_blend)
+
+
+def test_buffer_pool_byte_cap():
+    """the pinned pool is capped by BYTES once the ring's minimum exists, not only by frame count."""
+    from video_restore_b200.pipeline import BufferPool
+
+    made = []
+    pool = BufferPool(count=10, alloc=lambda s: (made.append(s), np.empty(s, np.uint8))[1], min_count=3, max_bytes=4 * 100)
+    bufs = [pool.get((10, 10)) for _ in range(3)]       # the minimum is always granted (3 x 100 bytes)
+    bufs.append(pool.get((10, 10)))                     # 4 x 100 <= cap
+    assert len(made) == 4
+
+    got = []
+    t = threading.Thread(target=lambda: got.append(pool.get((10, 10))), daemon=True)   # a fifth would exceed the cap: waits
+    t.start()
+    time.sleep(0.3)
+    assert not got and len(made) == 4
+    pool.release(bufs.pop())
+    t.join(2.0)
+    assert got and len(made) == 4                       # it got the released buffer, nothing new was pinned
