@@ -143,3 +143,67 @@ def test_frame_digests_are_order_defined():
     d1 = {0: frame_digest(a), 1: frame_digest(b)}
     d2 = {1: frame_digest(b), 0: frame_digest(a)}      # arrival order of the ranks does not matter
     assert combine_digests(d1) == combine_digests(d2) != combine_digests({0: d1[1], 1: d1[0]})
+
+
+def _fake_ffmpeg(tmp_path, body: str):
+    """A stand-in `ffmpeg` executable: records its argv, then runs `body` (python) with `argv` in scope."""
+    import stat
+    import sys
+
+    exe = tmp_path / "ffmpeg"
+    exe.write_text(f"#!{sys.executable}\nimport sys, json\nargv = sys.argv[1:]\n"
+                   f"open({str(tmp_path / 'argv.json')!r}, 'w').write(json.dumps(argv))\n{body}\n")
+    exe.chmod(exe.stat().st_mode | stat.S_IEXEC)
+    return str(exe)
+
+
+def test_copy_audio_muxes_through_ffmpeg_and_keeps_the_video_on_failure(tmp_path):
+    """cli.copy_audio = the reference's _copy_audio (video_upscaler.py:604-627): video of the output + audio of the input,
+    both copied, through a temp file that replaces the output; any failure leaves the output as written."""
+    import json
+
+    from video_restore_b200.cli import copy_audio
+
+    src, dst = tmp_path / "in.mp4", tmp_path / "out.mp4"
+    src.write_bytes(b"source-with-audio")
+    dst.write_bytes(b"video-only")
+    ok_bin = _fake_ffmpeg(tmp_path, "open(argv[-1], 'wb').write(b'muxed')")
+    assert copy_audio(str(src), str(dst), ffmpeg_bin=ok_bin) is True
+    assert dst.read_bytes() == b"muxed"
+    argv = json.loads((tmp_path / "argv.json").read_text())
+    i = [k for k, a in enumerate(argv) if a == "-i"]
+    assert [argv[k + 1] for k in i] == [str(dst), str(src)]          # input 0 = our video, input 1 = the source
+    assert argv[argv.index("-map") + 1] == "0:v" and "1:a" in argv   # video from ours, audio from the source
+    assert argv[argv.index("-c:v") + 1] == "copy" and argv[argv.index("-c:a") + 1] == "copy"
+    assert argv[-1] == str(dst) + ".temp.mp4" and not (tmp_path / "out.mp4.temp.mp4").exists()
+    # no audio track / ffmpeg error: non-zero exit -> output untouched, temp removed
+    dst.write_bytes(b"video-only")
+    bad_bin = _fake_ffmpeg(tmp_path, "open(argv[-1], 'wb').write(b'partial'); sys.exit(1)")
+    assert copy_audio(str(src), str(dst), ffmpeg_bin=bad_bin) is False
+    assert dst.read_bytes() == b"video-only" and not (tmp_path / "out.mp4.temp.mp4").exists()
+    # no binary at all: nothing happens
+    assert copy_audio(str(src), str(dst), ffmpeg_bin=str(tmp_path / "absent")) is False
+    assert dst.read_bytes() == b"video-only"
+
+
+def test_join_segments_uses_the_concat_demuxer_and_removes_the_parts(tmp_path):
+    import json
+
+    from video_restore_b200.cli import join_segments
+
+    parts = [tmp_path / f"out.part{i}.mp4" for i in range(3)]
+    for i, p in enumerate(parts):
+        p.write_bytes(b"seg%d" % i)
+    out = tmp_path / "out.mp4"
+    body = ("lst = argv[argv.index('-i') + 1]\n"
+            "names = [l.split(\"'\")[1] for l in open(lst).read().splitlines()]\n"
+            "open(argv[-1], 'wb').write(b''.join(open(n, 'rb').read() for n in names))")
+    assert join_segments([str(p) for p in parts], str(out), ffmpeg_bin=_fake_ffmpeg(tmp_path, body)) is True
+    assert out.read_bytes() == b"seg0seg1seg2" and not any(p.exists() for p in parts)
+    argv = json.loads((tmp_path / "argv.json").read_text())
+    assert argv[argv.index("-f") + 1] == "concat" and argv[argv.index("-c") + 1] == "copy"
+    # failure keeps the parts
+    for i, p in enumerate(parts):
+        p.write_bytes(b"seg%d" % i)
+    assert join_segments([str(p) for p in parts], str(out), ffmpeg_bin=_fake_ffmpeg(tmp_path, "sys.exit(2)")) is False
+    assert all(p.exists() for p in parts)

@@ -1,7 +1,7 @@
 """Command-line surface of the reference's video_upscaler.py (argparse at video_upscaler.py:649-682, presets at
 :687-701, config at :704-718), driving the B200 hot path. Only the flag surface and the per-frame stage are
-reproduced: the reference's ffmpeg decode/encode pipes, progress bar and audio mux (video_upscaler.py:143-281,
-:507-627) are out of scope. Video I/O is OpenCV VideoCapture / VideoWriter, frames flow through
+reproduced: the reference's ffmpeg decode/encode pipes and progress bar (video_upscaler.py:143-281, :507-602) are out
+of scope; the audio mux (:604-627) is `copy_audio`, run when the `ffmpeg` binary is on PATH. Video I/O is OpenCV VideoCapture / VideoWriter, frames flow through
 the in-process multi-GPU pipeline of pipeline.py (one thread + restorer per `--gpus` id, contiguous frame chunks,
 ordered bounded reassembly: N2), `--batch` walks a directory (N4), `--synthetic N` runs N generated 720p frames
 without any video I/O.
@@ -13,6 +13,7 @@ Flags added on top of the reference's parser are the README-only ones the north 
 from __future__ import annotations
 
 import argparse
+import shutil
 import sys
 import time
 from dataclasses import dataclass, field
@@ -161,6 +162,63 @@ def _run_one(cfg: OptimizedConfig, opts, source, sink, chunk: int, state_dict):
     return run_pipeline(source, sink, lambda gpu_id: make_restorer(cfg, gpu_id, state_dict), cfg.gpu_ids, opts, chunk=chunk)
 
 
+def copy_audio(input_path: str, output_path: str, ffmpeg_bin: str | None = None) -> bool:
+    """Mux the source's audio track into the written video without re-encoding either stream -- what the reference's
+    `_copy_audio` does through ffmpeg-python (video_upscaler.py:604-627): video stream of `output_path` + audio stream of
+    `input_path` -> temp file -> replaces `output_path`. Like the reference, a clip without an audio track (or any ffmpeg
+    failure) leaves the video as written and removes the temp file. Returns True when the mux happened. Needs the
+    `ffmpeg` binary on PATH; returns False (video kept) when it is absent."""
+    import os
+    import shutil
+    import subprocess
+
+    exe = ffmpeg_bin or shutil.which("ffmpeg")
+    if not exe:
+        return False
+    root, ext = os.path.splitext(output_path)
+    temp_path = output_path + ".temp" + (ext or ".mp4")  # the reference's name: output + '.temp.mp4'
+    cmd = [exe, "-y", "-loglevel", "error", "-i", output_path, "-i", input_path, "-map", "0:v", "-map", "1:a",
+           "-c:v", "copy", "-c:a", "copy", temp_path]
+    try:
+        done = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False)
+        if done.returncode == 0 and os.path.exists(temp_path) and os.path.getsize(temp_path) > 0:
+            os.replace(temp_path, output_path)
+            return True
+    except OSError:
+        pass
+    if os.path.exists(temp_path):
+        os.remove(temp_path)
+    return False
+
+
+def join_segments(segments, output_path: str, ffmpeg_bin: str | None = None) -> bool:
+    """Concatenate the per-rank video segments of `--procs` (consecutive frame ranges, same codec and size) into one file
+    with ffmpeg's concat demuxer, streams copied. Returns False (segments kept) without the `ffmpeg` binary or on failure."""
+    import os
+    import subprocess
+    import tempfile
+
+    exe = ffmpeg_bin or shutil.which("ffmpeg")
+    if not exe or not segments:
+        return False
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        for seg in segments:
+            f.write("file '%s'\n" % os.path.abspath(seg).replace("'", "'\\''"))
+        listing = f.name
+    try:
+        done = subprocess.run([exe, "-y", "-loglevel", "error", "-f", "concat", "-safe", "0", "-i", listing, "-c", "copy",
+                               output_path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False)
+        ok = done.returncode == 0 and os.path.exists(output_path) and os.path.getsize(output_path) > 0
+    except OSError:
+        ok = False
+    os.remove(listing)
+    if ok:
+        for seg in segments:
+            if os.path.abspath(seg) != os.path.abspath(output_path) and os.path.exists(seg):
+                os.remove(seg)
+    return ok
+
+
 def main(argv=None) -> int:
     args = build_parser().parse_args(argv)
     cfg = config_from_args(args)
@@ -195,7 +253,8 @@ def main(argv=None) -> int:
     ignored = [f for f, v in (("--crf", args.crf), ("--preset", args.preset)) if v is not None]
     print("[video-restore] note: video is written with OpenCV ('mp4v'), not libx264"
           + (f" -- {', '.join(ignored)} ignored" if ignored else "")
-          + ("" if args.no_audio else "; audio is NOT copied (needs the ffmpeg binary, absent here; video_upscaler.py:604-627)"))
+          + ("" if args.no_audio or shutil.which("ffmpeg") else "; audio is NOT copied (no ffmpeg binary on PATH; "
+                                                                  "video_upscaler.py:604-627)"))
     if args.enhanced:
         print("[video-restore] note: --enhanced also enables the README's seamless blend / temporal / CLAHE / unsharp stage, which "
               "the reference's code does not implement (--no-seamless --no-temporal --no-color-enhance --sharpen 0 turn it off)")
@@ -232,8 +291,9 @@ def main(argv=None) -> int:
             print(f"Error: {src_path.name}: no frames decoded")
             rc = 1
             continue
+        muxed = cfg.audio_copy and copy_audio(str(src_path), str(dst_path))  # :421-423
         print(f"{src_path.name}: processed {st.frames} frames in {st.seconds:.2f} s ({st.fps:.2f} fps) on "
-              f"{len(cfg.gpu_ids)} GPU(s)")
+              f"{len(cfg.gpu_ids)} GPU(s)" + ("; audio copied" if muxed else ""))
     return rc
 
 

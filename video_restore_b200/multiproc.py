@@ -209,8 +209,14 @@ def run_processes(args, cfg, opts) -> int:
             continue
         print(f"{src_path.name}: processed {res['frames']} frames in {res['seconds']:.2f} s ({res['fps']:.2f} fps) on "
               f"{len(cfg.gpu_ids)} GPU(s), one process per GPU")
-        print("segments (consecutive frame ranges; join with `ffmpeg -f concat -safe 0 -i list.txt -c copy "
-              f"{dst_path}`, list.txt = one `file '<segment>'` line each):")
+        from .cli import copy_audio, join_segments
+
+        if join_segments(res["segments"], str(dst_path)):
+            muxed = cfg.audio_copy and copy_audio(str(src_path), str(dst_path))
+            print(f"  joined {len(res['segments'])} segments into {dst_path}" + ("; audio copied" if muxed else ""))
+            continue
+        print("segments (consecutive frame ranges; no ffmpeg binary on PATH -- join with `ffmpeg -f concat -safe 0 -i list.txt "
+              f"-c copy {dst_path}`, list.txt = one `file '<segment>'` line each):")
         for s in res["segments"]:
             print(f"  {s}")
     return rc
