@@ -172,7 +172,7 @@ def test_tile_grid_bit_exact(gpu_lib):
         assert np.array_equal(tile_grid(*c), g[f"grid_{i}"]) and np.array_equal(tile_grid(*c), o_tile_grid(*c))
 
 
-@pytest.mark.parametrize("shape", [(97, 131), (64, 64), (5, 7), (240, 427), (96, 128), (80, 256), (128, 384)])
+@pytest.mark.parametrize("shape", [(97, 131), (64, 64), (5, 7), (240, 427), (96, 128), (80, 256), (128, 384), (150, 448), (24, 192)])
 def test_filters_bit_exact_vs_oracle(gpu_lib, shape):
     from oracle import filters as OF
     from video_restore_b200 import restorer as R
@@ -434,6 +434,28 @@ def test_full_size_720p_x4plus_runs_and_is_tile_consistent(gpu_lib):
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     assert a.shape == (2880, 5120, 3) and d.max() <= 1 and (d > 0).mean() < 4e-2
     assert a.std() > 2.0
+
+
+@pytest.mark.parametrize("H,W,tile,pad", [(90, 132, 32, 8), (61, 77, 32, 10), (150, 40, 16, 4), (64, 200, 48, 10), (37, 53, 64, 6)])
+@pytest.mark.parametrize("blend", ["gaussian", "crop"])
+def test_merge_fast_kernels_are_bit_identical(gpu_lib, monkeypatch, H, W, tile, pad, blend):
+    """The aligned tile-merge kernels (Gaussian blend: 4 pixels per thread, per-tile work hoisted, multiply-high division;
+    crop: 4 pixels per thread) against the general per-pixel kernels (VR_BLEND_FAST=0) on the same network output: same
+    tiles in the same order, same roundings."""
+    from video_restore_b200.restorer import FrameRestorer
+
+    name = "RealESRGAN_x4_v3"
+    sd = random_state_dict(name, seed=3)
+    f = synth_frame(H, W, seed=5)
+    outs = []
+    for fast in ("1", "0"):
+        monkeypatch.setenv("VR_BLEND_FAST", fast)
+        r = FrameRestorer(name, sd, tile=tile, tile_pad=pad, blend=blend)
+        outs.append(r.process_frame(f))
+        r.close()
+    monkeypatch.delenv("VR_BLEND_FAST")
+    assert outs[0].shape == (4 * H, 4 * W, 3)
+    assert np.array_equal(outs[0], outs[1])
 
 
 def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):

@@ -717,6 +717,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_FOLD_UP")) h->dev.fold_upsample = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_PHASES1")) h->dev.fuse_phases = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_BLEND_FAST")) h->dev.blend_fast = std::atoi(e) != 0;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->dev.stream, cudaStreamNonBlocking) != cudaSuccess)
         return bad("cudaStreamCreate failed", VR_E_CUDA);

@@ -32,6 +32,12 @@ __device__ __forceinline__ void store_px16(uint8_t* p, const Px16& v) {
     d[2] = v.q[2];
 }
 __device__ __forceinline__ uint8_t sat_u8(int v) { return static_cast<uint8_t>(min(max(v, 0), 255)); }
+// sat_u8(__float2int_rn(v)) in one instruction (F2IP.U8.F32): round half to even, clamp to [0, 255], NaN -> 0
+__device__ __forceinline__ uint32_t f2u8(float v) {
+    uint32_t r;
+    asm("cvt.rni.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -52,9 +58,9 @@ temporal_vec_kernel(const uint8_t* __restrict__ cur, const uint8_t* __restrict__
         const int p0 = p.b[3 * k], p1 = p.b[3 * k + 1], p2 = p.b[3 * k + 2];
         const int d = max(max(abs(c0 - p0), abs(c1 - p1)), abs(c2 - p2));
         if (static_cast<float>(d) < tau) {
-            o.b[3 * k] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c0)), __fmul_rn(alpha, static_cast<float>(p0)))));
-            o.b[3 * k + 1] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c1)), __fmul_rn(alpha, static_cast<float>(p1)))));
-            o.b[3 * k + 2] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c2)), __fmul_rn(alpha, static_cast<float>(p2)))));
+            o.b[3 * k] = f2u8((__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c0)), __fmul_rn(alpha, static_cast<float>(p0)))));
+            o.b[3 * k + 1] = f2u8((__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c1)), __fmul_rn(alpha, static_cast<float>(p1)))));
+            o.b[3 * k + 2] = f2u8((__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c2)), __fmul_rn(alpha, static_cast<float>(p2)))));
         } else {
             o.b[3 * k] = c.b[3 * k];
             o.b[3 * k + 1] = c.b[3 * k + 1];
@@ -118,7 +124,7 @@ clahe_hist_vec_kernel(const uint8_t* __restrict__ src, int64_t sstride, int tile
 // kTemporal: the temporal stage fused in -- the un-blended result (next frame's "previous") goes to dst, the frame blended with
 // `prev` to `blended`: one pass instead of two (reads src + prev, writes dst + blended; the separate temporal kernel re-read dst).
 template <bool kTemporal>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kTemporal ? 3 : 5)
 clahe_apply_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
                        const uint8_t* __restrict__ lut, int tiles_x, int tiles_y, float inv_tw, float inv_th,
                        const uint8_t* __restrict__ prev, uint8_t* __restrict__ blended, float alpha, float one_minus, float tau) {
@@ -155,7 +161,7 @@ clahe_apply_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ ds
         const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
         const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
         const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-        const int Yn = min(max(__float2int_rn(res), 0), 255);
+        const int Yn = static_cast<int>(f2u8(res));
         const int crd = cr - 128, cbd = cb - 128;
         o.b[3 * k] = sat_u8(Yn + ((cbd * 29049 + 8192) >> 14));
         o.b[3 * k + 1] = sat_u8(Yn + ((cbd * -5636 + crd * -11698 + 8192) >> 14));
@@ -171,9 +177,9 @@ clahe_apply_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ ds
             const int p0 = p.b[3 * k], p1 = p.b[3 * k + 1], p2 = p.b[3 * k + 2];
             const int d = max(max(abs(c0 - p0), abs(c1 - p1)), abs(c2 - p2));
             if (static_cast<float>(d) < tau) {
-                t.b[3 * k] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c0)), __fmul_rn(alpha, static_cast<float>(p0)))));
-                t.b[3 * k + 1] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c1)), __fmul_rn(alpha, static_cast<float>(p1)))));
-                t.b[3 * k + 2] = sat_u8(__float2int_rn(__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c2)), __fmul_rn(alpha, static_cast<float>(p2)))));
+                t.b[3 * k] = f2u8((__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c0)), __fmul_rn(alpha, static_cast<float>(p0)))));
+                t.b[3 * k + 1] = f2u8((__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c1)), __fmul_rn(alpha, static_cast<float>(p1)))));
+                t.b[3 * k + 2] = f2u8((__fadd_rn(__fmul_rn(one_minus, static_cast<float>(c2)), __fmul_rn(alpha, static_cast<float>(p2)))));
             } else {
                 t.b[3 * k] = o.b[3 * k];
                 t.b[3 * k + 1] = o.b[3 * k + 1];
@@ -215,37 +221,70 @@ int launch_clahe_apply_vec(Device& dev, const uint8_t* src, uint8_t* dst, int H,
 }
 
 // ------------------------------------------------------------------------------------------------
-// unsharp: 64 x 16 output pixels per block. fp32 input tile (22 x 70 px) and horizontal-pass tile in smem; the
-// vertical pass reads float4 columns and produces 4 rows x 4 bytes per thread (32-bit stores).
+// unsharp: 64 x 24 output pixels per block of 192 threads. fp32 input tile (30 rows x 216 floats) and horizontal-pass tile
+// (30 x 192) in shared memory; every shared-memory access is a 128-bit one, and laid out so that the eight lanes of a
+// quarter warp hit eight different 16-byte bank groups (row pitches of 55 and 49 float4: odd, so lanes that differ in the
+// ROW do not collide; ncu on the first version of this kernel: 30 % of its shared-memory wavefronts were bank conflicts and
+// the LSU pipe was 75 % busy -- shared-memory bandwidth, not HBM and not FP32 issue, was the limiter):
+//   load        aligned 128-bit global loads, all of a thread's loads in flight together -> sixteen floats -> four float4
+//               stores; lane L writes its four words in the order (s + L/2) & 3 so neighbouring lanes differ in bank group
+//   horizontal  one item = 16 consecutive output BYTES of one row, lanes walk down the rows: ten float4 loads (the 34 inputs
+//               its taps touch), four float4 stores -- 14 wavefronts per 16 outputs (4-byte items: 32)
+//   vertical    one item = 6 rows x 4 consecutive bytes: twelve float4 loads, six 32-bit global stores; 192 items = one per thread
+// What remains is instruction issue: the spec (oracle/filters.py unsharp_mask) is fp32 with a separate rounding after every
+// multiply and every add, i.e. 13 x 1.25 (halo rows) + 13 + 3 FP32 instructions per output byte that no FMA can merge.
 // ------------------------------------------------------------------------------------------------
-constexpr int kUvW = 64, kUvH = 16, kUvR = 3;
-constexpr int kUvInPitch = 216;  // 3 pad + (64 + 6) * 3 + 3 pad floats: centre pixel of output byte e sits at e + 12
+constexpr int kUvW = 64, kUvH = 24, kUvR = 3, kUvThreads = 192;
+constexpr int kUvCols = 216;     // staged floats per row: bytes -12 .. 203 of the row relative to the block's first byte
+constexpr int kUvInPitch = 220;  // 55 float4
+constexpr int kUvHPitch = 196;   // 49 float4 (192 used)
+constexpr int kUvTh = kUvH + 2 * kUvR;
+constexpr int kUvSmem = kUvTh * (kUvInPitch + kUvHPitch) * 4;  // 49 920 B: dynamic (above the 48 KB static limit)
 __constant__ float c_taps7v[7];
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kUvThreads)
 unsharp_vec_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int W, uint8_t* __restrict__ dst,
                    int64_t dstride, float amount) {
-    __shared__ __align__(16) float s_in[kUvH + 2 * kUvR][kUvInPitch];
-    __shared__ __align__(16) float s_h[kUvH + 2 * kUvR][kUvW * 3];
+    constexpr int th = kUvTh, tw = kUvW + 2 * kUvR;
+    extern __shared__ __align__(16) float s_uv[];
+    float (*s_in)[kUvInPitch] = reinterpret_cast<float (*)[kUvInPitch]>(s_uv);  // centre pixel of output byte e sits at e + 12
+    float (*s_h)[kUvHPitch] = reinterpret_cast<float (*)[kUvHPitch]>(s_uv + th * kUvInPitch);
     const int tid = threadIdx.x;
     const int bx0 = blockIdx.x * kUvW, by0 = blockIdx.y * kUvH;
-    constexpr int th = kUvH + 2 * kUvR, tw = kUvW + 2 * kUvR;
-    const bool interior = bx0 >= 4 && bx0 + kUvW + 4 <= W && by0 >= kUvR && by0 + kUvH + kUvR <= H;
+    const bool interior = bx0 >= 6 && bx0 + kUvW + 6 <= W && by0 >= kUvR && by0 + kUvH + kUvR <= H;
     if (interior) {
-        // aligned 32-bit loads: the row segment starts at byte bx0*3 - 9; read from bx0*3 - 12 (4-aligned: W % 4 == 0)
-        constexpr int kWords = (tw * 3 + 3 + 3) / 4;  // 54 words cover bytes [-12, 204)
-        for (int i = tid; i < th * kWords; i += 256) {
-            const int ty = i / kWords, wq = i - ty * kWords;
-            const uint32_t wv = __ldg(reinterpret_cast<const uint32_t*>(src + (by0 - kUvR + ty) * sstride +
-                                                                         static_cast<int64_t>(bx0) * 3 - 12) + wq);
-            float* o = &s_in[ty][wq * 4];  // byte j of the segment (from -12) -> s_in[.][j]; pixel data starts at j = 3
-            o[0] = static_cast<float>(wv & 0xff);
-            o[1] = static_cast<float>((wv >> 8) & 0xff);
-            o[2] = static_cast<float>((wv >> 16) & 0xff);
-            o[3] = static_cast<float>(wv >> 24);
+        // the row segment bytes [-16, 208) around the block = 14 x 16 bytes; floats 4 .. 219 of it are kept (column = float - 4)
+        constexpr int kQuads = 14, kIters = (th * kQuads + kUvThreads - 1) / kUvThreads;
+        uint4 qv[kIters];
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) {
+            const int i = tid + k * kUvThreads;
+            if (i < th * kQuads) {
+                const int ty = i / kQuads, q4 = i - ty * kQuads;
+                qv[k] = __ldg(reinterpret_cast<const uint4*>(src + (by0 - kUvR + ty) * sstride + static_cast<int64_t>(bx0) * 3 - 16) + q4);
+            }
+        }
+        const int rot = (tid & 31) >> 1;
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) {
+            const int i = tid + k * kUvThreads;
+            if (i < th * kQuads) {
+                const int ty = i / kQuads, q4 = i - ty * kQuads;
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+                    const int m = (st + rot) & 3;
+                    const uint32_t wv = m == 0 ? qv[k].x : m == 1 ? qv[k].y : m == 2 ? qv[k].z : qv[k].w;
+                    const int col = q4 * 16 + m * 4 - 4;
+                    if (col >= 0 && col < kUvCols)
+                        *reinterpret_cast<float4*>(&s_in[ty][col]) =
+                            make_float4(static_cast<float>(wv & 0xff), static_cast<float>((wv >> 8) & 0xff),
+                                        static_cast<float>((wv >> 16) & 0xff), static_cast<float>(wv >> 24));
+                }
+            }
         }
     } else {
-        for (int i = tid; i < th * tw; i += 256) {
+#pragma unroll 4
+        for (int i = tid; i < th * tw; i += kUvThreads) {
             const int ty = i / tw, tx = i - ty * tw;
             int sy = by0 - kUvR + ty, sx = bx0 - kUvR + tx;
             // REFLECT_101
@@ -257,38 +296,48 @@ unsharp_vec_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int 
             s_in[ty][3 + tx * 3 + 1] = static_cast<float>(p[1]);
             s_in[ty][3 + tx * 3 + 2] = static_cast<float>(p[2]);
         }
+        // floats 0..2 and 213..215 of a row stay unwritten here: the float4 loads below fetch them, no tap uses them
     }
     __syncthreads();
-    // horizontal pass: one item = 4 consecutive pixels of one channel in one row (10 loads for 4 outputs)
-    constexpr int kItemsRow = (kUvW / 4) * 3;
-    for (int i = tid; i < th * kItemsRow; i += 256) {
-        const int ty = i / kItemsRow, j = i - ty * kItemsRow;
-        const int c = j % 3, g = j / 3;
-        const float* in = &s_in[ty][3 + g * 12 + c];  // input pixel (4g - 3 + 3) .. : tap t of output q reads in[(q + t) * 3]
-        float x[10];
+    // horizontal pass: output byte e reads the same channel of pixels -3 .. +3, i.e. s_in[e + 3 + 3 t], t = 0 .. 6
+    constexpr int kWide = 16, kGroups = kUvW * 3 / kWide;  // 12 items per row
+    for (int i = tid; i < th * kGroups; i += kUvThreads) {
+        const int g = i / th, ty = i - g * th;  // consecutive lanes: consecutive rows
+        const float4* in4 = reinterpret_cast<const float4*>(&s_in[ty][g * kWide]);
+        float x[kWide + 24];
 #pragma unroll
-        for (int t = 0; t < 10; ++t) x[t] = in[t * 3];
+        for (int v = 0; v < (kWide + 24) / 4; ++v) {
+            const float4 f = in4[v];
+            x[4 * v] = f.x;
+            x[4 * v + 1] = f.y;
+            x[4 * v + 2] = f.z;
+            x[4 * v + 3] = f.w;
+        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float h = __fmul_rn(c_taps7v[0], x[q]);
+        for (int q4 = 0; q4 < kWide / 4; ++q4) {
+            float h[4];
 #pragma unroll
-            for (int t = 1; t < 7; ++t) h = __fadd_rn(h, __fmul_rn(c_taps7v[t], x[q + t]));
-            s_h[ty][(g * 4 + q) * 3 + c] = h;
+            for (int q = 0; q < 4; ++q) {
+                h[q] = __fmul_rn(c_taps7v[0], x[q4 * 4 + q + 3]);
+#pragma unroll
+                for (int t = 1; t < 7; ++t) h[q] = __fadd_rn(h[q], __fmul_rn(c_taps7v[t], x[q4 * 4 + q + 3 + 3 * t]));
+            }
+            *reinterpret_cast<float4*>(&s_h[ty][g * kWide + q4 * 4]) = make_float4(h[0], h[1], h[2], h[3]);
         }
     }
     __syncthreads();
-    // vertical pass: one item = 4 rows x 4 consecutive output bytes
+    // vertical pass: one item = kUvRows rows x 4 consecutive output bytes
+    constexpr int kUvRows = 6, kColGroups = kUvW * 3 / 4;  // 48
     const float one_plus = __fadd_rn(1.0f, amount);
-    constexpr int kColGroups = kUvW * 3 / 4;  // 48
-    for (int i = tid; i < (kUvH / 4) * kColGroups; i += 256) {
+    for (int i = tid; i < (kUvH / kUvRows) * kColGroups; i += kUvThreads) {
         const int rg = i / kColGroups, cg = i - rg * kColGroups;
-        float4 hv[10];
+        float4 hv[kUvRows + 6];
 #pragma unroll
-        for (int t = 0; t < 10; ++t) hv[t] = *reinterpret_cast<const float4*>(&s_h[rg * 4 + t][cg * 4]);
+        for (int t = 0; t < kUvRows + 6; ++t) hv[t] = *reinterpret_cast<const float4*>(&s_h[rg * kUvRows + t][cg * 4]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int y = by0 + rg * 4 + q;
-            const float4 xin = *reinterpret_cast<const float4*>(&s_in[rg * 4 + q + kUvR][cg * 4 + 12]);
+        for (int q = 0; q < kUvRows; ++q) {
+            const int y = by0 + rg * kUvRows + q;
+            const float4 xin = *reinterpret_cast<const float4*>(&s_in[rg * kUvRows + q + kUvR][cg * 4 + 12]);
             float v[4], xi[4] = {xin.x, xin.y, xin.z, xin.w};
             const float* h0 = reinterpret_cast<const float*>(&hv[q]);
 #pragma unroll
@@ -303,7 +352,7 @@ unsharp_vec_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float o = __fsub_rn(__fmul_rn(one_plus, xi[e]), __fmul_rn(amount, v[e]));
-                packed |= static_cast<uint32_t>(sat_u8(__float2int_rn(o))) << (8 * e);
+                packed |= f2u8(o) << (8 * e);
             }
             if (y < H && bx0 * 3 + cg * 4 + 3 < W * 3)
                 *reinterpret_cast<uint32_t*>(dst + y * dstride + static_cast<int64_t>(bx0) * 3 + cg * 4) = packed;
@@ -312,7 +361,7 @@ unsharp_vec_kernel(const uint8_t* __restrict__ src, int64_t sstride, int H, int 
 }
 bool try_unsharp_vec(Device& dev, const uint8_t* src, int64_t sstride, int H, int W, uint8_t* dst, int64_t dstride,
                      float amount, int* rc) {
-    if (W % 64 != 0 || sstride % 4 != 0 || dstride % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 3) ||
+    if (W % 64 != 0 || sstride % 16 != 0 || dstride % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) ||
         (reinterpret_cast<uintptr_t>(dst) & 3) || H < 2 || W < 2)
         return false;
     static bool taps_done[64] = {};
@@ -330,10 +379,15 @@ bool try_unsharp_vec(Device& dev, const uint8_t* src, int64_t sstride, int H, in
             *rc = -2;
             return true;
         }
+        if (cudaFuncSetAttribute(unsharp_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUvSmem) != cudaSuccess) {
+            set_error(dev.err, "unsharp_vec: cudaFuncSetAttribute failed");
+            *rc = -2;
+            return true;
+        }
         taps_done[dev.ordinal & 63] = true;
     }
     dim3 grid(W / kUvW, (H + kUvH - 1) / kUvH);
-    unsharp_vec_kernel<<<grid, 256, 0, dev.stream>>>(src, sstride, H, W, dst, dstride, amount);
+    unsharp_vec_kernel<<<grid, kUvThreads, kUvSmem, dev.stream>>>(src, sstride, H, W, dst, dstride, amount);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error(dev.err, std::string("unsharp_vec: ") + cudaGetErrorString(e));

@@ -103,6 +103,7 @@ struct Device {
     // so off by default. Kept as the base of the per-RDB persistent kernel.
     bool multi_layer = false;
     bool fold_upsample = true;     // VR_FOLD_UP=0: materialise nearest x2 and run conv_up1/2 as plain 3x3 convs
+    bool blend_fast = true;        // VR_BLEND_FAST=0: the general Gaussian-blend kernel on aligned frames too (A/B runs, tests)
     bool fuse_phases = true;       // VR_PHASES1=0: the four phases of a folded upsample conv as four launches (A/B runs)
     bool weights_resident = true;  // VR_WRES=0: always stream weights with the activations
     // VR_ROLL bit mask: which NHWC 3x3 layers run on the rolling-row kernels K2 / K3 instead of the tiled kernel K1:
