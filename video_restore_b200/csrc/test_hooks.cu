@@ -453,8 +453,9 @@ extern "C" int vr_filter_bench(int32_t device, int32_t kind, int32_t H, int32_t 
     cudaMalloc(&table, 4096);
     const size_t tile_elems = static_cast<size_t>(H) * W * 4;
     if (kind >= 4) {
-        VR_CUDA_CHECK(cudaMalloc(&t0, kind == 7 ? static_cast<size_t>(H) * W * 4 * 64 * 2 : tile_elems * 2), dev.err);
-        VR_CUDA_CHECK(cudaMemset(t0, 0x38, tile_elems * 2), dev.err);
+        const size_t t0_bytes = kind == 7 ? static_cast<size_t>(H) * W * 4 * 64 * 2 : kind == 5 ? tile_elems * 4 : tile_elems * 2;
+        VR_CUDA_CHECK(cudaMalloc(&t0, t0_bytes), dev.err);
+        VR_CUDA_CHECK(cudaMemset(t0, 0x38, kind == 5 ? t0_bytes : tile_elems * 2), dev.err);
         if (kind == 7 || kind == 6) VR_CUDA_CHECK(cudaMalloc(&t1, static_cast<size_t>(H) * W * 64 * 2), dev.err);
     }
     auto run = [&]() -> int {
@@ -465,15 +466,24 @@ extern "C" int vr_filter_bench(int32_t device, int32_t kind, int32_t H, int32_t 
             case 3: return launch_temporal(dev, a, st, b, st, H, W, c, st, 0.2f, 12.f);
             case 4: return launch_post_crop(dev, t0, W, 0, 0, W, H, c, st, 0, 0);
             case 5: {
-                // four overlapping tiles covering the frame (pad = 64 output px), gather-blended
-                const int tw = W / 2, th = H / 2, pad = 64;
+                // the tile grid of the `--quality max` preset at x4 (tile 2048, pad 256 output pixels; square tiles, the
+                // last row / column smaller), every padded tile in its own region of t0, gather-blended
+                const int T = 2048, pad = 256;
+                const int ntx = (W + T - 1) / T, nty = (H + T - 1) / T;
                 std::vector<BlendTile> tiles;
-                for (int ty = 0; ty < 2; ++ty)
-                    for (int tx = 0; tx < 2; ++tx) {
-                        const int x0 = tx ? tw - pad : 0, y0 = ty ? th - pad : 0;
-                        tiles.push_back({t0, x0, y0, tw + pad, th + pad, tw + pad});
+                size_t off = 0;
+                for (int ty = 0; ty < nty; ++ty)
+                    for (int tx = 0; tx < ntx; ++tx) {
+                        const int x0 = std::max(tx * T - pad, 0), x1 = std::min((tx + 1) * T + pad, static_cast<int>(W));
+                        const int y0 = std::max(ty * T - pad, 0), y1 = std::min((ty + 1) * T + pad, static_cast<int>(H));
+                        tiles.push_back({t0 + off * 4, x0, y0, x1 - x0, y1 - y0, x1 - x0});
+                        off += static_cast<size_t>(x1 - x0) * (y1 - y0);
                     }
-                return launch_post_blend(dev, tiles, 2, 2, tw, pad, c, st, H, W, blend_state);
+                if (off > 2 * static_cast<size_t>(H) * W) {
+                    set_error(dev.err, "vr_filter_bench: blend tiles exceed the staging buffer");
+                    return VR_E_INVALID;
+                }
+                return launch_post_blend(dev, tiles, ntx, nty, T, pad, c, st, H, W, blend_state);
             }
             case 6: return launch_pre(dev, a, st, H, W, 0, 0, W, H, 0, t1, W, 0, 0);
             case 7: return launch_upsample2x(dev, t1, H, W, 64, reinterpret_cast<__half*>(t0));
