@@ -255,7 +255,7 @@ post_blend_kernel(const BlendTileDev* __restrict__ tiles, int tiles_x, int tiles
 // per-tile work hoisted out of the pixel loop -- candidate tile range once per thread (division by `tile_out` as one
 // multiply-high with a host-side reciprocal), one descriptor and one row weight per tile, four independent pixel loads in
 // flight. Per pixel the accumulation order (tiles in row-major order) and every rounding are those of post_blend_kernel, so
-// both are bit-exact against the oracle (`oracle/realesrganer.py` tile_process, gather form). ncu, 5120 x 2880: the general
+// both are bit-exact against the oracle (`oracle.realesrganer` tile_process, gather form). ncu, 5120 x 2880: the general
 // kernel executes 201 instructions per pixel (two integer divisions, a 48-byte descriptor and three IEEE divisions per pixel).
 __device__ __forceinline__ int div_magic(int x, uint32_t magic) { return static_cast<int>(__umulhi(static_cast<uint32_t>(x), magic)); }
 __global__ void __launch_bounds__(256)
