@@ -10,10 +10,10 @@ for w in c4_x4plus_720p_qmax_plain c1_x4plus_256_tile128 c2_x4v3_480p_fast c3_x2
 done
 python bench.py --steps 200 --no-cpu-baseline > $O/r2_bench_c4_enhanced_long.json 2>> $O/r2_bench.err
 python bench.py --steps 200 --no-cpu-baseline --workload c4_x4plus_720p_qmax_plain > $O/r2_bench_c4_plain_long.json 2>> $O/r2_bench.err
-python bench.py --impl reference > $O/r2_bench_reference_arm.json 2>> $O/r2_bench.err
+[ -n "$VR_SKIP_REF" ] || python bench.py --impl reference > $O/r2_bench_reference_arm.json 2>> $O/r2_bench.err
 python tools/bench_filters.py > $O/r2_filters_gbs.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/r2_ncu_launches_c4_enhanced.csv python tools/run_frames.py --workload c4_x4plus_720p_qmax_enhanced --frames 1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"conv3x3_pair" -s 13 -c 3 -o $O/r2_k4_rdb_enhanced -f python tools/run_frames.py --workload c4_x4plus_720p_qmax_enhanced --frames 1 > $O/r2_ncu_rdb_enh.log 2>&1
+[ -n "$VR_SKIP_REF" ] || ncu --set full --clock-control none --import-source on -k regex:"conv3x3_pair" -s 13 -c 3 -o $O/r2_k4_rdb_enhanced -f python tools/run_frames.py --workload c4_x4plus_720p_qmax_enhanced --frames 1 > $O/r2_ncu_rdb_enh.log 2>&1
 ncu --set full --clock-control none -k regex:"bilateral|pre_kernel|post_blend|unsharp|clahe|temporal" -s 8 -c 16 -o $O/r2_filters_innet -f python tools/run_frames.py --workload c4_x4plus_720p_qmax_enhanced --frames 2 > $O/r2_ncu_filters.log 2>&1
 python - <<PY
 import json, glob

@@ -39,55 +39,9 @@ struct Pair2 {
     static constexpr int kMinSlots = 4;
 };
 
-// The static box sequence of one work item: step s = A's row pair s (chunks 0..nchA-1), then B's row pair s - kLag (chunks
-// 0..nchA-1 from TMA, chunk nchA from the hand-off slot).
-struct Pair2Iter {
-    int nA2, nB2, nchA, S, lag;
-    int s, part, c;
-    __device__ __forceinline__ void init(int nin2B, int nch_a, int lag_) {
-        nB2 = nin2B >> 1;
-        nA2 = nB2 + 1;
-        nchA = nch_a;
-        lag = lag_;
-        S = nB2 + lag;
-        s = 0;
-        part = 0;
-        c = 0;
-        normalize();
-    }
-    __device__ __forceinline__ bool done() const { return s >= S; }
-    __device__ __forceinline__ void normalize() {
-        while (s < S) {
-            if (part == 0) {
-                if (s < nA2) return;
-                part = 1;
-                c = 0;
-            }
-            const int b = s - lag;
-            if (b >= 0 && b < nB2) return;
-            part = 0;
-            c = 0;
-            ++s;
-        }
-    }
-    __device__ __forceinline__ void next() {
-        const int n = part == 0 ? nchA : nchA + 1;
-        if (++c == n) {
-            c = 0;
-            if (part == 0) part = 1;
-            else {
-                part = 0;
-                ++s;
-            }
-            normalize();
-        }
-    }
-    __device__ __forceinline__ int pair_index() const { return part == 0 ? s : s - lag; }
-    __device__ __forceinline__ bool hand() const { return part == 1 && c == nchA; }
-    __device__ __forceinline__ bool last_chunk() const { return c == (part == 0 ? nchA - 1 : nchA); }
-    __device__ __forceinline__ int boxes() const { return nA2 * nchA + nB2 * (nchA + 1); }
-};
-
+// The static box sequence of one work item -- step s = A's row pair s (chunks 0..nchA-1), then B's row pair s - lag (chunks
+// 0..nchA-1 from TMA, chunk nchA from the hand-off slot) -- is walked incrementally by the producer, the waiter and the issuer
+// (three copies of the same few counters; a shared iterator struct cost registers in the issuing warps and was removed).
 // sub-items as in K3, strips of 126 pixels
 __device__ __forceinline__ PairSub pair2_sub(const ConvArgs& a, int u) { return pair_sub(a, u); }
 
