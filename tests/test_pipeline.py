@@ -311,6 +311,7 @@ def test_video_file_content_matches_oracle(tmp_path):
     import cv2
 
     from oracle.pipeline import OracleRestorer
+    from video_restore_b200.pipeline import VideoFileSink, VideoFileSource
     from video_restore_b200.restorer import FrameRestorer
     from video_restore_b200.synth import random_state_dict, synth_frame
 
