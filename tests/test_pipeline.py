@@ -454,3 +454,127 @@ def test_buffer_pool_byte_cap():
     pool.release(bufs.pop())
     t.join(2.0)
     assert got and len(made) == 4                       # it got the released buffer, nothing new was pinned
+
+
+# --- the reference's ffmpeg rawvideo pipes (video_upscaler.py:220-262, :514-532) against stand-in binaries ---------------
+_FAKE_FFPROBE = '''#!{py}
+import sys, json, numpy as np
+a = np.load(sys.argv[-1])
+assert "-count_frames" in sys.argv and "v:0" in sys.argv
+print(json.dumps({{"streams": [{{"width": a.shape[2], "height": a.shape[1], "r_frame_rate": "24000/1001", "nb_read_frames": str(a.shape[0])}}]}}))
+'''
+_FAKE_FFMPEG = '''#!{py}
+import sys, json, numpy as np
+argv = sys.argv[1:]
+if "-hwaccels" in argv:
+    print("Hardware acceleration methods:\\nvdpau\\n{hw}")
+    sys.exit(0)
+src = argv[argv.index("-i") + 1]
+if src == "-":                                   # encoder: raw BGR frames on stdin -> the "file"
+    data = sys.stdin.buffer.read()
+    open(argv[-1], "wb").write(data)
+    open(argv[-1] + ".argv.json", "w").write(json.dumps(argv))
+    sys.exit({enc_rc})
+assert argv[-1] == "-" and argv[argv.index("-pix_fmt") + 1] == "bgr24" and argv[argv.index("-f") + 1] == "rawvideo"
+open(src + ".decode_argv.json", "w").write(json.dumps(argv))
+try:                                             # decoder: every frame of the .npy "video" to stdout
+    sys.stdout.buffer.write(np.load(src).tobytes())
+    sys.stdout.buffer.flush()
+except BrokenPipeError:
+    pass
+'''
+
+
+def _fake_ffmpeg_tools(tmp_path, hw="", enc_rc=0):
+    import stat
+    import sys
+
+    d = tmp_path / "bin"
+    d.mkdir(exist_ok=True)
+    for name, body in (("ffprobe", _FAKE_FFPROBE.format(py=sys.executable)),
+                       ("ffmpeg", _FAKE_FFMPEG.format(py=sys.executable, hw=hw, enc_rc=enc_rc))):
+        f = d / name
+        f.write_text(body)
+        f.chmod(f.stat().st_mode | stat.S_IEXEC)
+    return str(d / "ffmpeg"), str(d / "ffprobe")
+
+
+def test_ffmpeg_pipe_source_counts_and_reads_exactly(tmp_path):
+    from video_restore_b200.pipeline import FfmpegPipeSource
+
+    ffmpeg, ffprobe = _fake_ffmpeg_tools(tmp_path, hw="cuda")
+    frames = clip(11)
+    video = tmp_path / "in.npy"
+    np.save(video, np.stack(frames))
+    src = FfmpegPipeSource(str(video), ffmpeg, ffprobe, lookahead=4)
+    assert len(src) == 11 and (src.height, src.width) == (12, 16) and abs(src.fps - 24000 / 1001) < 1e-9
+    assert src.hwaccel == "cuda"                                          # listed by `ffmpeg -hwaccels` (:264-278)
+    # interleaved chunks through the shared front-to-back decoder
+    r0, r1 = src.reader(), src.reader()
+    got = {}
+    for rd, (a, b) in ((r0, (0, 3)), (r1, (3, 6)), (r0, (6, 9)), (r1, (9, 14))):
+        for i, f in zip(range(a, b), rd.read_range(a, b)):
+            got[i] = f
+    assert sorted(got) == list(range(11)) and all(np.array_equal(got[i], frames[i]) for i in got)   # EOF ends the last range
+    src.close()
+    import json
+
+    argv = json.loads((tmp_path / "in.npy.decode_argv.json").read_text())
+    assert argv.index("-hwaccel") < argv.index("-i") and argv[argv.index("-hwaccel") + 1] == "cuda"  # before the input (:227)
+    # one long range per worker: a decoder process of its own, exact forward skipping, going back re-opens
+    rd = src.reader(long_ranges=True)
+    assert all(np.array_equal(a, b) for a, b in zip(rd.read_range(7, 10), frames[7:10]))
+    assert all(np.array_equal(a, b) for a, b in zip(rd.read_range(2, 4), frames[2:4]))
+    rd.cap.release()
+    with pytest.raises(RuntimeError, match="Failed to read video info"):
+        FfmpegPipeSource(str(tmp_path / "missing.npy"), ffmpeg, ffprobe)
+
+
+def test_ffmpeg_pipe_sink_and_pipeline_roundtrip(tmp_path):
+    """ffmpeg decode pipe -> three chunked workers -> ordered reassembly -> ffmpeg libx264 encode pipe (stand-in binaries: the
+    'encoded file' is the raw byte stream the encoder was fed)."""
+    import json
+
+    from video_restore_b200.pipeline import FfmpegPipeSink, FfmpegPipeSource
+
+    ffmpeg, ffprobe = _fake_ffmpeg_tools(tmp_path)
+    frames = clip(13)
+    video, out = tmp_path / "in.npy", tmp_path / "out.mp4"
+    np.save(video, np.stack(frames))
+    opts = FrameOpts(temporal=True)
+    src = FfmpegPipeSource(str(video), ffmpeg, ffprobe)
+    assert src.hwaccel is None
+    st = run_pipeline(src, FfmpegPipeSink(str(out), src.fps, crf=12, preset="veryslow", ffmpeg_bin=ffmpeg), lambda g: StubRestorer(g),
+                      [0, 1, 2], opts, chunk=2, temporal_blend=stub_blend)
+    assert st.frames == 13
+    want = np.stack(sequential(frames, opts))
+    assert out.read_bytes() == want.tobytes()                             # every frame, in order, bit for bit
+    argv = json.loads((tmp_path / "out.mp4.argv.json").read_text())
+    for flag, val in (("-s", "32x24"), ("-vcodec", "rawvideo"), ("-crf", "12"), ("-preset", "veryslow"), ("-r", str(src.fps)),
+                      ("-movflags", "+faststart")):
+        assert argv[argv.index(flag) + 1] == val, flag
+    assert "libx264" in argv and "-an" in argv and argv.count("-pix_fmt") == 2 and argv[-1] == str(out)
+    # an encoder that fails is an error, not a silently short file
+    bad, _ = _fake_ffmpeg_tools(tmp_path, enc_rc=3)
+    sink = FfmpegPipeSink(str(out), 24.0, ffmpeg_bin=bad)
+    sink.write(0, want[0])
+    with pytest.raises(OSError, match="exited with 3"):
+        sink.close()
+
+
+def test_video_io_selection(tmp_path, monkeypatch):
+    from video_restore_b200 import pipeline as P
+
+    ffmpeg, _ = _fake_ffmpeg_tools(tmp_path)
+    video = tmp_path / "in.npy"
+    np.save(video, np.stack(clip(3)))
+    monkeypatch.setenv("PATH", str(tmp_path / "bin"))
+    assert P.find_ffmpeg() == (ffmpeg, str(tmp_path / "bin" / "ffprobe"))
+    assert isinstance(P.open_video_source(str(video)), P.FfmpegPipeSource)
+    assert isinstance(P.open_video_sink(str(tmp_path / "o.mp4"), 24.0, 18, "fast"), P.FfmpegPipeSink)
+    monkeypatch.setenv("VR_IO", "cv2")                                    # force OpenCV
+    assert P.find_ffmpeg() is None
+    assert isinstance(P.open_video_sink(str(tmp_path / "o.mp4"), 24.0), P.VideoFileSink)
+    monkeypatch.delenv("VR_IO")
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))                 # no binaries: OpenCV
+    assert P.find_ffmpeg() is None

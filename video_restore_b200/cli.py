@@ -1,10 +1,11 @@
 """Command-line surface of the reference's video_upscaler.py (argparse at video_upscaler.py:649-682, presets at
 :687-701, config at :704-718), driving the B200 hot path. Only the flag surface and the per-frame stage are
-reproduced: the reference's ffmpeg decode/encode pipes and progress bar (video_upscaler.py:143-281, :507-602) are out
-of scope; the audio mux (:604-627) is `copy_audio`, run when the `ffmpeg` binary is on PATH. Video I/O is OpenCV VideoCapture / VideoWriter, frames flow through
-the in-process multi-GPU pipeline of pipeline.py (one thread + restorer per `--gpus` id, contiguous frame chunks,
-ordered bounded reassembly: N2), `--batch` walks a directory (N4), `--synthetic N` runs N generated 720p frames
-without any video I/O.
+reproduced; the progress bar (video_upscaler.py:569-602) is out of scope. Video I/O is the
+reference's ffmpeg rawvideo pipes (pipeline.FfmpegPipeSource / FfmpegPipeSink: `-hwaccel` decode :220-262, libx264
+`-crf` / `-preset` encode :514-532) and its audio mux (:604-627, `copy_audio`) when the `ffmpeg` and `ffprobe` binaries
+are on PATH, otherwise OpenCV VideoCapture / VideoWriter. Frames flow through the in-process multi-GPU pipeline of
+pipeline.py (one thread + restorer per `--gpus` id, contiguous frame chunks, ordered bounded reassembly: N2),
+`--batch` walks a directory (N4), `--synthetic N` runs N generated 720p frames without any video I/O.
 
 Flags added on top of the reference's parser are the README-only ones the north star names:
   --model RealESRGAN_x2plus (README.md:158), --denoise S, --sharpen A (README.md:140-141),
@@ -225,7 +226,7 @@ def main(argv=None) -> int:
     opts = frame_opts_from_config(cfg)
     import torch
 
-    from .pipeline import NullSink, SyntheticSource, VideoFileSink, VideoFileSource
+    from .pipeline import NullSink, SyntheticSource, find_ffmpeg, open_video_sink, open_video_source
 
     if not cfg.gpu_ids:
         cfg.gpu_ids = list(range(torch.cuda.device_count()))
@@ -249,12 +250,16 @@ def main(argv=None) -> int:
         print(f"processed {st.frames} frames in {st.seconds:.2f} s ({st.fps:.2f} fps) on {len(cfg.gpu_ids)} GPU(s); "
               f"{st.boundary_frames} boundary frames exchanged; model set-up {st.setup_seconds:.1f} s")
         return 0
-    # what this build does NOT do with the reference's flags: said once, loudly, instead of silently ignoring them
-    ignored = [f for f, v in (("--crf", args.crf), ("--preset", args.preset)) if v is not None]
-    print("[video-restore] note: video is written with OpenCV ('mp4v'), not libx264"
-          + (f" -- {', '.join(ignored)} ignored" if ignored else "")
-          + ("" if args.no_audio or shutil.which("ffmpeg") else "; audio is NOT copied (no ffmpeg binary on PATH; "
-                                                                  "video_upscaler.py:604-627)"))
+    # video I/O: the reference's ffmpeg rawvideo pipes (libx264, --crf / --preset honoured, audio copied) when the binaries are on
+    # PATH; otherwise OpenCV -- and then what is NOT done with the reference's flags is said once, loudly
+    if find_ffmpeg():
+        print(f"[video-restore] video I/O through ffmpeg pipes: libx264 -crf {cfg.crf} -preset {cfg.preset}"
+              + ("" if args.no_audio else ", audio copied from the source"))
+    else:
+        ignored = [f for f, v in (("--crf", args.crf), ("--preset", args.preset)) if v is not None]
+        print("[video-restore] note: no ffmpeg / ffprobe on PATH -- video is read and written with OpenCV ('mp4v'), not libx264"
+              + (f" -- {', '.join(ignored)} ignored" if ignored else "")
+              + ("" if args.no_audio else "; audio is NOT copied (video_upscaler.py:604-627)"))
     if args.enhanced:
         print("[video-restore] note: --enhanced also enables the README's seamless blend / temporal / CLAHE / unsharp stage, which "
               "the reference's code does not implement (--no-seamless --no-temporal --no-color-enhance --sharpen 0 turn it off)")
@@ -278,8 +283,8 @@ def main(argv=None) -> int:
     for src_path, dst_path in jobs:
         # like process_video (:369-428): a failing clip is reported and the batch goes on
         try:
-            source = VideoFileSource(str(src_path))
-            st = _run_one(cfg, opts, source, VideoFileSink(str(dst_path), source.fps), chunk, state_dict)
+            source = open_video_source(str(src_path))
+            st = _run_one(cfg, opts, source, open_video_sink(str(dst_path), source.fps, cfg.crf, cfg.preset), chunk, state_dict)
         except KeyboardInterrupt:
             print("\n\nProcessing interrupted")
             return 1

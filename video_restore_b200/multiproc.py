@@ -52,7 +52,7 @@ def _worker(rank: int, world: int, port: int, job: dict, result_q) -> None:
     import torch.distributed as dist
 
     from .cli import OptimizedConfig, make_restorer
-    from .pipeline import SyntheticSource, VideoFileSink, _VideoReader
+    from .pipeline import FfmpegPipeSink, SyntheticSource, VideoFileSink, _PipeCapture, _VideoReader
     from .restorer import FrameOpts
     from .sharder import FrameRangeSharder
 
@@ -66,16 +66,26 @@ def _worker(rank: int, world: int, port: int, job: dict, result_q) -> None:
         restorer = make_restorer(cfg, gpu, allow_random=job["allow_random"])
         total = job["total"]
         sh = FrameRangeSharder(rank, world, total)
+        io = job.get("io")  # {"ffmpeg", "hwaccel"} when the parent found the binaries: the reference's rawvideo pipes, else OpenCV
+
+        def open_reader():
+            # every rank decodes its own range with a decoder of its own and exact forward skipping
+            if io:
+                return _VideoReader(job["input"], "grab", lambda: _PipeCapture(io["ffmpeg"], job["input"], job["width"],
+                                                                                 job["height"], io.get("hwaccel")))
+            return _VideoReader(job["input"], "grab")
+
         if job["synthetic"]:
             src = SyntheticSource(job["height"], job["width"], total, seed=1, distinct=8)
             reader = src.reader()
         else:
-            reader = _VideoReader(job["input"], "grab")
+            reader = open_reader()
         sink = None
         if job["output"]:
             out = Path(job["output"])
             seg = out.with_name(f"{out.stem}.part{rank:02d}{out.suffix}")
-            sink = VideoFileSink(str(seg), job["fps"])
+            sink = (FfmpegPipeSink(str(seg), job["fps"], cfg.crf, cfg.preset, io["ffmpeg"]) if io else
+                    VideoFileSink(str(seg), job["fps"]))
         digests = {}
         # set-up outside the clock: weights are resident, one frame has gone through (buffers, tensor maps, pinned rings),
         # the point-to-point connections are open
@@ -94,7 +104,7 @@ def _worker(rank: int, world: int, port: int, job: dict, result_q) -> None:
             # random access (the boundary frame of the in-order protocol): a decoder of its own, exact forward skipping
             if job["synthetic"]:
                 return next(iter(src.read_range(i, i + 1)))
-            return next(iter(_VideoReader(job["input"], "grab").read_range(i, i + 1)))
+            return next(iter(open_reader().read_range(i, i + 1)))
 
         def put_frame(i, o):
             digests[i] = frame_digest(o)
@@ -124,7 +134,7 @@ def _worker(rank: int, world: int, port: int, job: dict, result_q) -> None:
 
 
 def run_job(gpu_ids, cfg, opts, total: int, synthetic: bool, input_path=None, output_path=None, fps: float = 30.0,
-            height: int = 720, width: int = 1280, allow_random: bool = False) -> dict:
+            height: int = 720, width: int = 1280, allow_random: bool = False, io: dict | None = None) -> dict:
     """Run one clip on `gpu_ids`, one process each. Returns {frames, seconds, fps, digest, per_frame, exchange_ms, segments}."""
     import dataclasses
 
@@ -135,7 +145,7 @@ def run_job(gpu_ids, cfg, opts, total: int, synthetic: bool, input_path=None, ou
         raise ValueError(f"{total} frames for {world} processes: use fewer GPUs")
     job = {"gpu_ids": list(gpu_ids), "cfg": {**dataclasses.asdict(cfg), "gpu_ids": list(gpu_ids)},
            "opts": dataclasses.asdict(opts), "total": int(total), "synthetic": bool(synthetic), "input": input_path,
-           "output": output_path, "fps": float(fps), "height": height, "width": width, "allow_random": allow_random}
+           "output": output_path, "fps": float(fps), "height": height, "width": width, "allow_random": allow_random, "io": io}
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -174,7 +184,7 @@ def run_job(gpu_ids, cfg, opts, total: int, synthetic: bool, input_path=None, ou
 
 def run_processes(args, cfg, opts) -> int:
     """CLI entry (cli.main with --procs)."""
-    from .pipeline import VideoFileSource
+    from .pipeline import FfmpegPipeSource, open_video_source
 
     allow_random = bool(args.random_weights or args.synthetic > 0)
     if args.synthetic > 0:
@@ -200,9 +210,10 @@ def run_processes(args, cfg, opts) -> int:
     rc = 0
     for src_path, dst_path in jobs:
         try:
-            src = VideoFileSource(str(src_path))  # counts the frames exactly, once, for every rank
-            res = run_job(cfg.gpu_ids, cfg, opts, len(src), False, str(src_path), str(dst_path), src.fps,
-                          allow_random=allow_random)
+            src = open_video_source(str(src_path))  # counts the frames exactly, once, for every rank
+            io = {"ffmpeg": src.ffmpeg, "hwaccel": src.hwaccel} if isinstance(src, FfmpegPipeSource) else None
+            res = run_job(cfg.gpu_ids, cfg, opts, len(src), False, str(src_path), str(dst_path), src.fps, height=src.height,
+                          width=src.width, allow_random=allow_random, io=io)
         except Exception as e:  # noqa: BLE001 - like the reference's process_video: report and go on
             print(f"Error: {src_path.name}: {e}")
             rc = 1

@@ -148,10 +148,12 @@ class _SequentialDecoder:
     """One thread decoding the file front to back into a bounded index -> frame map; consumers take frames by index (each
     frame once; frame 0 stays available for the workers' warm-up reads)."""
 
-    def __init__(self, path: str, lookahead: int):
-        import cv2
+    def __init__(self, path: str, lookahead: int, open_capture: Optional[Callable[[], object]] = None):
+        if open_capture is None:
+            import cv2
 
-        self._cap = cv2.VideoCapture(path)
+            open_capture = lambda: cv2.VideoCapture(path)  # noqa: E731
+        self._cap = open_capture()
         self._cv = threading.Condition()
         self._frames: dict = {}
         self._first = None
@@ -227,12 +229,17 @@ class _SharedReader:
 
 
 class _VideoReader:
-    def __init__(self, path: str, seek: str = "grab"):
-        import cv2
+    def __init__(self, path: str, seek: str = "grab", open_capture: Optional[Callable[[], object]] = None):
+        if open_capture is None:
+            import cv2
 
-        self._cv2 = cv2
+            self._cv2 = cv2
+            open_capture = lambda: cv2.VideoCapture(path)  # noqa: E731
+        elif seek == "set":
+            raise ValueError("a pipe cannot seek: use seek='grab'")
+        self._open = open_capture
         self.path, self.seek = path, seek
-        self.cap = cv2.VideoCapture(path)
+        self.cap = open_capture()
         self.pos = 0
 
     def read_range(self, start: int, end: int):
@@ -243,7 +250,7 @@ class _VideoReader:
             else:
                 if self.pos > start:  # chunks come in increasing order per worker; re-open if a caller goes back
                     self.cap.release()
-                    self.cap = self._cv2.VideoCapture(self.path)
+                    self.cap = self._open()
                     self.pos = 0
                 while self.pos < start:
                     if not self.cap.grab():
@@ -255,6 +262,169 @@ class _VideoReader:
                 return
             self.pos += 1
             yield frame
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ffmpeg pipes: the reference's own decode / encode hand-off (video_upscaler.py:220-262, :514-532), used when the binaries exist
+# ---------------------------------------------------------------------------------------------------------------
+def find_ffmpeg() -> Optional[tuple]:
+    """(ffmpeg, ffprobe) when both binaries are on PATH and VR_IO is not 'cv2', else None."""
+    import os
+    import shutil
+
+    if os.environ.get("VR_IO", "").lower() == "cv2":
+        return None
+    a, b = shutil.which("ffmpeg"), shutil.which("ffprobe")
+    return (a, b) if a and b else None
+
+
+class _PipeCapture:
+    """The `read` / `grab` / `release` part of cv2.VideoCapture over `ffmpeg -i <path> -f rawvideo -pix_fmt bgr24 -`: the
+    decoder process writes whole BGR frames to its stdout, a short read is the end of the stream (:243-247)."""
+
+    def __init__(self, exe: str, path: str, width: int, height: int, hwaccel: Optional[str] = None):
+        import subprocess
+
+        cmd = [exe, "-loglevel", "error"]
+        if hwaccel:  # must precede the input (:227-229)
+            cmd += ["-hwaccel", hwaccel]
+        cmd += ["-i", path, "-f", "rawvideo", "-pix_fmt", "bgr24", "-"]
+        self.shape = (height, width, 3)
+        self.nbytes = height * width * 3
+        self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
+
+    def _read_exact(self) -> Optional[bytearray]:
+        buf = bytearray(self.nbytes)
+        view, got = memoryview(buf), 0
+        while got < self.nbytes:
+            n = self.proc.stdout.readinto(view[got:])
+            if not n:
+                return None
+            got += n
+        return buf
+
+    def read(self):
+        if self.proc is None:
+            return False, None
+        buf = self._read_exact()
+        if buf is None:
+            return False, None
+        return True, np.frombuffer(buf, np.uint8).reshape(self.shape)
+
+    def grab(self) -> bool:
+        return self.read()[0]
+
+    def release(self) -> None:
+        if self.proc is not None:
+            self.proc.stdout.close()
+            self.proc.terminate()
+            self.proc.wait()
+            self.proc = None
+
+
+class FfmpegPipeSource:
+    """A video file decoded by the `ffmpeg` binary through a rawvideo pipe, as the reference does. Stream facts and the EXACT
+    frame count come from one `ffprobe -count_frames` call (the reference's last-resort counter, :195-203, used first here:
+    the chunk plan needs the true length). `-hwaccel cuda` / `nvdec` is requested when `ffmpeg -hwaccels` lists it (:264-278).
+    Same reader contract as VideoFileSource: one shared front-to-back decoder for interleaved chunks, one forward-skipping
+    decoder process per worker for long ranges."""
+
+    def __init__(self, path: str, ffmpeg_bin: Optional[str] = None, ffprobe_bin: Optional[str] = None, lookahead: int = 256):
+        import json
+        import subprocess
+
+        found = find_ffmpeg()
+        self.ffmpeg = ffmpeg_bin or (found[0] if found else None)
+        self.ffprobe = ffprobe_bin or (found[1] if found else None)
+        if not self.ffmpeg or not self.ffprobe:
+            raise OSError("ffmpeg / ffprobe not found")
+        self.path, self.lookahead = str(path), int(lookahead)
+        done = subprocess.run([self.ffprobe, "-v", "error", "-select_streams", "v:0", "-count_frames", "-show_entries",
+                               "stream=width,height,r_frame_rate,nb_read_frames", "-of", "json", self.path],
+                              capture_output=True, text=True, check=False)
+        try:
+            st = json.loads(done.stdout)["streams"][0]
+            self.width, self.height = int(st["width"]), int(st["height"])
+            num, _, den = str(st["r_frame_rate"]).partition("/")
+            self.fps = float(num) / float(den or 1)
+            self.n = int(st["nb_read_frames"])
+        except Exception as e:  # noqa: BLE001 - the reference's message (:213)
+            raise RuntimeError(f"Failed to read video info: {e}") from e
+        self.hwaccel = self._detect_hwaccel()
+        self._dispatch = None
+        self._lock = threading.Lock()
+
+    def _detect_hwaccel(self) -> Optional[str]:
+        import subprocess
+
+        try:
+            out = subprocess.run([self.ffmpeg, "-hwaccels"], capture_output=True, text=True, check=False).stdout
+        except OSError:
+            return None
+        return "cuda" if "cuda" in out else "nvdec" if "nvdec" in out else None
+
+    def _open(self) -> _PipeCapture:
+        return _PipeCapture(self.ffmpeg, self.path, self.width, self.height, self.hwaccel)
+
+    def __len__(self) -> int:
+        return self.n
+
+    def reader(self, long_ranges: bool = False):
+        if not long_ranges:
+            with self._lock:
+                if self._dispatch is None:
+                    self._dispatch = _SequentialDecoder(self.path, self.lookahead, self._open)
+            return _SharedReader(self._dispatch)
+        return _VideoReader(self.path, "grab", self._open)
+
+    def close(self) -> None:
+        if self._dispatch is not None:
+            self._dispatch.stop()
+            self._dispatch = None
+
+
+class FfmpegPipeSink:
+    """libx264 through the `ffmpeg` binary, fed raw BGR frames on stdin -- the reference's encoder (:514-532): `-crf`, `-preset`,
+    yuv420p, +faststart. Frames must arrive in order (the reassembler guarantees it)."""
+
+    def __init__(self, path: str, fps: float, crf: int = 15, preset: str = "slow", ffmpeg_bin: Optional[str] = None):
+        found = find_ffmpeg()
+        self.exe = ffmpeg_bin or (found[0] if found else None)
+        if not self.exe:
+            raise OSError("ffmpeg not found")
+        self.path, self.fps, self.crf, self.preset = str(path), fps, int(crf), str(preset)
+        self.proc = None
+
+    def write(self, index: int, frame: np.ndarray) -> None:
+        import subprocess
+
+        if self.proc is None:
+            h, w = frame.shape[:2]
+            cmd = [self.exe, "-y", "-loglevel", "error", "-f", "rawvideo", "-vcodec", "rawvideo", "-s", f"{w}x{h}", "-pix_fmt", "bgr24",
+                   "-r", str(self.fps), "-i", "-", "-an", "-vcodec", "libx264", "-crf", str(self.crf), "-preset", self.preset,
+                   "-pix_fmt", "yuv420p", "-movflags", "+faststart", self.path]
+            self.proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        try:
+            self.proc.stdin.write(np.ascontiguousarray(frame).data)
+        except BrokenPipeError as e:
+            raise OSError(f"ffmpeg stopped reading while encoding {self.path} (exit {self.proc.poll()})") from e
+
+    def close(self) -> None:
+        if self.proc is not None:
+            self.proc.stdin.close()
+            rc = self.proc.wait()
+            self.proc = None
+            if rc != 0:
+                raise OSError(f"ffmpeg exited with {rc} while encoding {self.path}")
+
+
+def open_video_source(path: str):
+    """The reference's ffmpeg pipe when the binaries are on PATH, OpenCV otherwise (VR_IO=cv2 forces OpenCV)."""
+    return FfmpegPipeSource(path) if find_ffmpeg() else VideoFileSource(path)
+
+
+def open_video_sink(path: str, fps: float, crf: int = 15, preset: str = "slow"):
+    return FfmpegPipeSink(path, fps, crf, preset) if find_ffmpeg() else VideoFileSink(path, fps)
 
 
 class NullSink:
