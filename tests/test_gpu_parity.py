@@ -509,6 +509,11 @@ def test_execution_variants_are_bit_identical(gpu_lib, monkeypatch):
     # as several atlases. K1 is position-independent: bit-identical; the rolling-row kernels within one level
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_ATLAS_TILES": "1"})[0])
     assert np.array_equal(base, run({"VR_ROLL": "0", "VR_ATLAS_TILES": "2"})[0])
+    # automatic group sizing: a memory budget too small for the whole atlas splits it into groups by itself (one 160 x 160 tile
+    # of this frame needs ~155 MB of activations), a generous one changes nothing
+    small, n_small = run({"VR_ROLL": "0", "VR_MEM_BUDGET_MB": "200"})
+    assert np.array_equal(base, small) and n_small > 3 * n_base
+    assert run({"VR_ROLL": "0", "VR_MEM_BUDGET_MB": "100000"})[1] == n_base
     g2 = run({"VR_ATLAS_TILES": "2"})[0]
     d = np.abs(g2.astype(np.int32) - k4.astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 3e-2

@@ -76,6 +76,9 @@ struct vr_handle {
     std::map<std::string, ConvWeights> layers;
     bool committed = false;
     int atlas_tiles = 8;  // tiles per atlas axis (VR_ATLAS_TILES, read at vr_create)
+    bool atlas_forced = false;   // VR_ATLAS_TILES given: no automatic sizing
+    size_t mem_budget = 0;       // bytes the activations of ONE atlas group may take (0.8 x free memory at vr_create, or VR_MEM_BUDGET_MB)
+    int auto_H = 0, auto_W = 0, auto_group = 8;  // automatic group size of the last frame geometry
     Gaps gaps;        // atlas gap mask of the frame being processed (read by conv())
     int gap_shift = 0;  // log2 of the current layer's resolution multiple
     int atlas_w = 0, atlas_h = 0;
@@ -490,7 +493,27 @@ int restore_enqueue(vr_handle* h, const uint8_t* d_bgr, int H, int W, int64_t st
     }
     // VR_ATLAS_TILES (1..8, default 8): tiles per atlas axis. Activation memory is proportional to the atlas, not to the frame: a
     // smaller group bounds it the way `--tile-size` bounds it in the reference (same result, more launches).
-    const int kGroup = h->atlas_tiles;
+    int kGroup = h->atlas_tiles;
+    if (!h->atlas_forced && h->mem_budget > 0) {
+        // automatic: the largest group (<= 8 tiles per axis) whose activations fit the budget. Bytes per network-input pixel of an
+        // RRDBNet group: in32 64 + feat 128 + trunk 128 + 3 dense-block buffers 3 x 384 + HR buffers (4 + 16 + 16) x 128 (+ 4 x 128
+        // without the folded upsample) + the fp16 RGB4 output 16 x 8; the SRVGG network needs less (the figure is an upper bound)
+        if (h->auto_H != H || h->auto_W != W) {
+            const size_t per_px = 64 + 128 + 128 + 3 * 384 + (4 + 16 + 16) * 128 + (h->dev.fold_upsample ? 0 : 4 * 128) + 16 * 8;
+            int g = 8;
+            for (; g > 1; --g) {
+                size_t wa = 0, ha = 0;
+                for (int j = 0; j < std::min(g, tiles_x); ++j) wa += (grid[j].pad_x1 - grid[j].pad_x0) / net_div + 1;
+                for (int i = 0; i < std::min(g, tiles_y); ++i)
+                    ha += (grid[static_cast<size_t>(i) * tiles_x].pad_y1 - grid[static_cast<size_t>(i) * tiles_x].pad_y0) / net_div + 1;
+                if (wa * ha * per_px <= h->mem_budget) break;
+            }
+            h->auto_H = H;
+            h->auto_W = W;
+            h->auto_group = g;
+        }
+        kGroup = std::min(kGroup, h->auto_group);
+    }
     const int groups_x = (tiles_x + kGroup - 1) / kGroup, groups_y = (tiles_y + kGroup - 1) / kGroup;
     if (h->tile_out.size() < static_cast<size_t>(groups_x) * groups_y) h->tile_out.resize(static_cast<size_t>(groups_x) * groups_y);
     std::vector<BlendTile> btiles(blend ? grid.size() : 0);
@@ -712,6 +735,7 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     if (const char* e = std::getenv("VR_ATLAS_TILES")) {
         const int v = std::atoi(e);
         h->atlas_tiles = v < 1 ? 1 : (v > 8 ? 8 : v);
+        h->atlas_forced = true;
     }
     if (const char* e = std::getenv("VR_PLANAR")) h->dev.planar = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_MULTI")) h->dev.multi_layer = std::atoi(e) != 0;
@@ -719,6 +743,13 @@ int vr_create(const vr_config* cfg, vr_handle** out) {
     if (const char* e = std::getenv("VR_PHASES1")) h->dev.fuse_phases = std::atoi(e) != 0;
     if (const char* e = std::getenv("VR_BLEND_FAST")) h->dev.blend_fast = std::atoi(e) != 0;
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bad("cudaSetDevice failed", VR_E_CUDA);
+    {
+        // memory the activations of one atlas group may take: the tile atlas keeps a whole group's activations resident (the
+        // reference's `--tile-size` bounds memory per tile), so frames whose full atlas would not fit are run as several groups
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) h->mem_budget = free_b / 10 * 8;
+        if (const char* e = std::getenv("VR_MEM_BUDGET_MB")) h->mem_budget = static_cast<size_t>(std::atoll(e)) << 20;
+    }
     if (cudaStreamCreateWithFlags(&h->dev.stream, cudaStreamNonBlocking) != cudaSuccess)
         return bad("cudaStreamCreate failed", VR_E_CUDA);
     *out = h.release();
