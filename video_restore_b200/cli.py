@@ -16,7 +16,6 @@ from __future__ import annotations
 import argparse
 import shutil
 import sys
-import time
 from dataclasses import dataclass, field
 from pathlib import Path
 from typing import List, Optional
